@@ -1,0 +1,263 @@
+/*
+ * oracle/cpu_baseline.c — CPU BASELINE DRIVER (test/bench infrastructure, NOT product code).
+ *
+ * Times the reference's CPU arithmetic for the RS(k,m) encode / reconstruct path on host cores:
+ *
+ *   kind 0 "reference": the reference's own vendored SIMD kernel, compiled unmodified from
+ *          /root/reference/seaweed-volume/vendor/reed-solomon-erasure/simd_c/reedsolomon.c into
+ *          oracle/_ref/libref_rs_<isa>.so and driven exactly like code_some_slices
+ *          (rse/src/core.rs:484-512: for each input, for each output row: first input mul, the
+ *          rest mul_xor), in 256 KiB batches like encodeDataOneBatch
+ *          (weed/storage/erasure_coding/ec_encoder.go:68,248-278).
+ *   kind 1 "gfni port": a fused AVX-512/AVX2 + GFNI kernel (vgf2p8affineqb, all k inputs of a
+ *          64-byte column combined in registers into the m outputs) — a restatement of what
+ *          klauspost/reedsolomon v1.14.0 (go.mod:50, source not in the tree) runs on a GFNI CPU
+ *          (its mulGFNI_10x4_64 family).  Same matrix, same field; labelled "port".
+ *
+ * Threads split the byte-column range (the way klauspost splits an Encode across goroutines).
+ * The matrix rows are passed in, so the same driver serves encode (parity rows) and reconstruct
+ * (decode rows).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <immintrin.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rs_oracle.h"
+
+typedef size_t (*gal_fn)(const uint8_t low[16], const uint8_t high[16], const uint8_t *in,
+                         uint8_t *out, size_t len); /* rse/simd_c/reedsolomon.h:30-42 */
+
+static void *g_ref_handle;
+static gal_fn g_ref_mul, g_ref_mul_xor;
+static char g_ref_isa[32] = "none";
+
+/* Load oracle/_ref/libref_rs_<isa>.so for the best ISA this CPU supports. dir = oracle/_ref */
+int orc_ref_load(const char *dir)
+{
+    if (g_ref_handle) return 0;
+    __builtin_cpu_init();
+    const char *order[3];
+    int n = 0;
+    if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) order[n++] = "avx512";
+    if (__builtin_cpu_supports("avx2")) order[n++] = "avx2";
+    if (__builtin_cpu_supports("ssse3")) order[n++] = "ssse3";
+    for (int i = 0; i < n; i++) {
+        char path[4096];
+        snprintf(path, sizeof path, "%s/libref_rs_%s.so", dir, order[i]);
+        void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+        if (!h) continue;
+        g_ref_mul = (gal_fn)dlsym(h, "reedsolomon_gal_mul");
+        g_ref_mul_xor = (gal_fn)dlsym(h, "reedsolomon_gal_mul_xor");
+        if (g_ref_mul && g_ref_mul_xor) {
+            g_ref_handle = h;
+            snprintf(g_ref_isa, sizeof g_ref_isa, "%s", order[i]);
+            return 0;
+        }
+        dlclose(h);
+    }
+    return -1;
+}
+
+const char *orc_ref_isa(void) { return g_ref_isa; }
+
+int orc_cpu_has_gfni(void)
+{
+    __builtin_cpu_init();
+    if (!__builtin_cpu_supports("gfni")) return 0;
+    if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) return 2;
+    if (__builtin_cpu_supports("avx2")) return 1;
+    return 0;
+}
+
+/* The reference kernel handles whole vectors only and returns bytes done; the caller finishes the
+ * tail with the scalar loop (rse/src/galois_8.rs:291-327). */
+static void ref_mul(uint8_t c, const uint8_t *in, uint8_t *out, size_t n, int xor_into)
+{
+    uint8_t low[16], high[16];
+    orc_mul_table_half(c, low, high);
+    size_t done = xor_into ? g_ref_mul_xor(low, high, in, out, n) : g_ref_mul(low, high, in, out, n);
+    if (done < n) {
+        if (xor_into) orc_mul_slice_xor(c, in + done, out + done, n - done);
+        else orc_mul_slice(c, in + done, out + done, n - done);
+    }
+}
+
+/* 8×8 bit matrix A with gf2p8affineqb(x, A, 0) == c ⊗ x over 0x11D.
+ * Output bit i of each byte = parity(A.byte[7-i] & x) (Intel SDM, GF2P8AFFINEQB). */
+static uint64_t gfni_matrix(uint8_t c)
+{
+    uint64_t a = 0;
+    for (int i = 0; i < 8; i++) {
+        uint8_t row = 0;
+        for (int j = 0; j < 8; j++)
+            if ((orc_mul(c, (uint8_t)(1u << j)) >> i) & 1) row |= (uint8_t)(1u << j);
+        a |= (uint64_t)row << (8 * (7 - i));
+    }
+    return a;
+}
+
+__attribute__((target("avx512f,avx512bw,gfni")))
+static void gfni512_range(int k, int r, const uint64_t *mats /* r*k */, const uint8_t *const *in,
+                          uint8_t *const *out, size_t lo, size_t hi)
+{
+    size_t x = lo;
+    for (; x + 64 <= hi; x += 64) {
+        __m512i acc[ORC_MAX_SHARDS];
+        for (int i = 0; i < k; i++) {
+            __m512i v = _mm512_loadu_si512((const void *)(in[i] + x));
+            for (int p = 0; p < r; p++) {
+                __m512i t = _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[p * k + i]), 0);
+                acc[p] = i == 0 ? t : _mm512_xor_si512(acc[p], t);
+            }
+        }
+        for (int p = 0; p < r; p++) _mm512_storeu_si512((void *)(out[p] + x), acc[p]);
+    }
+    for (; x < hi; x++)
+        for (int p = 0; p < r; p++) {
+            uint8_t v = 0;
+            for (int i = 0; i < k; i++) {
+                /* scalar tail through the same bit matrices */
+                uint64_t a = mats[p * k + i];
+                uint8_t b = in[i][x], o = 0;
+                for (int bit = 0; bit < 8; bit++)
+                    o |= (uint8_t)(__builtin_parity((unsigned)((a >> (8 * (7 - bit))) & 0xff) & b) << bit);
+                v ^= o;
+            }
+            out[p][x] = v;
+        }
+}
+
+/* RS(10,4)-shaped fast path: 4 accumulators live in registers across the 10 inputs. */
+__attribute__((target("avx512f,avx512bw,gfni")))
+static void gfni512_range_r4(int k, const uint64_t *mats, const uint8_t *const *in,
+                             uint8_t *const *out, size_t lo, size_t hi)
+{
+    size_t x = lo;
+    for (; x + 64 <= hi; x += 64) {
+        __m512i v = _mm512_loadu_si512((const void *)(in[0] + x));
+        __m512i a0 = _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[0 * k]), 0);
+        __m512i a1 = _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[1 * k]), 0);
+        __m512i a2 = _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[2 * k]), 0);
+        __m512i a3 = _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[3 * k]), 0);
+        for (int i = 1; i < k; i++) {
+            v = _mm512_loadu_si512((const void *)(in[i] + x));
+            a0 = _mm512_xor_si512(a0, _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[0 * k + i]), 0));
+            a1 = _mm512_xor_si512(a1, _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[1 * k + i]), 0));
+            a2 = _mm512_xor_si512(a2, _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[2 * k + i]), 0));
+            a3 = _mm512_xor_si512(a3, _mm512_gf2p8affine_epi64_epi8(v, _mm512_set1_epi64((long long)mats[3 * k + i]), 0));
+        }
+        _mm512_stream_si512((void *)(out[0] + x), a0);
+        _mm512_stream_si512((void *)(out[1] + x), a1);
+        _mm512_stream_si512((void *)(out[2] + x), a2);
+        _mm512_stream_si512((void *)(out[3] + x), a3);
+    }
+    if (x < hi) gfni512_range(k, 4, mats, in, out, x, hi);
+}
+
+__attribute__((target("avx2,gfni")))
+static void gfni256_range(int k, int r, const uint64_t *mats, const uint8_t *const *in,
+                          uint8_t *const *out, size_t lo, size_t hi)
+{
+    size_t x = lo;
+    for (; x + 32 <= hi; x += 32) {
+        __m256i acc[ORC_MAX_SHARDS];
+        for (int i = 0; i < k; i++) {
+            __m256i v = _mm256_loadu_si256((const __m256i *)(in[i] + x));
+            for (int p = 0; p < r; p++) {
+                __m256i t = _mm256_gf2p8affine_epi64_epi8(v, _mm256_set1_epi64x((long long)mats[p * k + i]), 0);
+                acc[p] = i == 0 ? t : _mm256_xor_si256(acc[p], t);
+            }
+        }
+        for (int p = 0; p < r; p++) _mm256_storeu_si256((__m256i *)(out[p] + x), acc[p]);
+    }
+    for (; x < hi; x++)
+        for (int p = 0; p < r; p++) {
+            uint8_t v = 0;
+            for (int i = 0; i < k; i++) {
+                uint64_t a = mats[p * k + i];
+                uint8_t b = in[i][x], o = 0;
+                for (int bit = 0; bit < 8; bit++)
+                    o |= (uint8_t)(__builtin_parity((unsigned)((a >> (8 * (7 - bit))) & 0xff) & b) << bit);
+                v ^= o;
+            }
+            out[p][x] = v;
+        }
+}
+
+typedef struct {
+    int kind, k, r;
+    const uint8_t *rows;  /* r*k coefficients */
+    const uint64_t *mats; /* r*k gfni matrices (kind 1) */
+    const uint8_t *const *in;
+    uint8_t *const *out;
+    size_t lo, hi, batch;
+} job_t;
+
+static void *worker(void *arg)
+{
+    job_t *j = (job_t *)arg;
+    if (j->kind == 0) {
+        /* code_some_slices over batches of `batch` bytes (256 KiB in production) */
+        for (size_t b = j->lo; b < j->hi; b += j->batch) {
+            size_t n = j->hi - b < j->batch ? j->hi - b : j->batch;
+            for (int i = 0; i < j->k; i++)
+                for (int p = 0; p < j->r; p++)
+                    ref_mul(j->rows[p * j->k + i], j->in[i] + b, j->out[p] + b, n, i != 0);
+        }
+    } else {
+        int lvl = orc_cpu_has_gfni();
+        if (lvl == 2) {
+            if (j->r == 4 && (((uintptr_t)j->out[0] | (uintptr_t)j->out[1] | (uintptr_t)j->out[2] |
+                               (uintptr_t)j->out[3] | j->lo) & 63) == 0)
+                gfni512_range_r4(j->k, j->mats, j->in, j->out, j->lo, j->hi);
+            else
+                gfni512_range(j->k, j->r, j->mats, j->in, j->out, j->lo, j->hi);
+        } else {
+            gfni256_range(j->k, j->r, j->mats, j->in, j->out, j->lo, j->hi);
+        }
+    }
+    return NULL;
+}
+
+/*
+ * out[p][x] = XOR_i rows[p*k+i] ⊗ in[i][x] for x in [0,n), split over `threads` threads.
+ * kind 0 = reference kernel (needs orc_ref_load), kind 1 = gfni port.  0 ok; -1 unavailable.
+ */
+int orc_cpu_apply_mt(int kind, int k, int r, const uint8_t *rows, const uint8_t *const *in,
+                     uint8_t *const *out, size_t n, int threads, size_t batch)
+{
+    if (kind == 0 && !g_ref_handle) return -1;
+    if (kind == 1 && !orc_cpu_has_gfni()) return -1;
+    if (threads < 1) threads = 1;
+    if (batch == 0) batch = 256 * 1024;
+    uint64_t *mats = NULL;
+    if (kind == 1) {
+        mats = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)r * k);
+        for (int i = 0; i < r * k; i++) mats[i] = gfni_matrix(rows[i]);
+    }
+    /* per-thread ranges in multiples of 4 KiB so streaming stores stay aligned */
+    size_t unit = 4096, units = (n + unit - 1) / unit;
+    job_t *jobs = (job_t *)calloc((size_t)threads, sizeof(job_t));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    int started = 0;
+    for (int t = 0; t < threads; t++) {
+        size_t lo = units * t / threads * unit, hi = units * (t + 1) / threads * unit;
+        if (hi > n) hi = n;
+        if (lo >= hi) continue;
+        jobs[started] = (job_t){kind, k, r, rows, mats, in, out, lo, hi, batch};
+        if (threads == 1) worker(&jobs[started]);
+        else pthread_create(&tids[started], NULL, worker, &jobs[started]);
+        started++;
+    }
+    if (threads > 1)
+        for (int t = 0; t < started; t++) pthread_join(tids[t], NULL);
+    free(jobs);
+    free(tids);
+    free(mats);
+    return 0;
+}
