@@ -1,0 +1,152 @@
+/*
+ * swec.h — C ABI of the B200-native Reed–Solomon erasure-coding engine for SeaweedFS.
+ *
+ * This is the drop-in boundary for the RS(10,4) hot path of weed/storage/erasure_coding:
+ * a thin cgo file binds these entry points in place of
+ * github.com/klauspost/reedsolomon (go.mod:50).  Plain pointers and sizes only; every function
+ * returns 0 (SWEC_OK) or a negative swec_status, never aborts, never falls back to the CPU: if
+ * no CUDA device / kernel image is usable the call fails with SWEC_ERR_NO_DEVICE / SWEC_ERR_CUDA
+ * so the caller's cleanup-on-error path runs (weed/server/volume_grpc_erasure_coding.go:78-87).
+ *
+ * Reference interface each group replaces (paths relative to the SeaweedFS tree):
+ *   swec_encoder_new            reedsolomon.New(ds, ps)   weed/storage/erasure_coding/ec_context.go:34-36,
+ *                                                          weed/storage/store_ec.go:485
+ *   swec_encode                 Encoder.Encode            weed/storage/erasure_coding/ec_encoder.go:265
+ *   swec_reconstruct            Encoder.Reconstruct       weed/storage/erasure_coding/ec_encoder.go:360
+ *                               Encoder.ReconstructData   weed/storage/store_ec.go:551   (data_only = 1)
+ *   swec_verify                 (Rust twin) rs.verify     seaweed-volume/src/storage/erasure_coding/ec_encoder.rs:177-278
+ *   swec_write_ec_files         WriteEcFiles / generateEcFiles   ec_encoder.go:61-69,110-128
+ *   swec_rebuild_ec_files       RebuildEcFiles / generateMissingEcFiles   ec_encoder.go:74-104,146-200
+ *   swec_write_dat_file         WriteDatFile              weed/storage/erasure_coding/ec_decoder.go:176-223
+ *   swec_locate_data            LocateData                weed/storage/erasure_coding/ec_locate.go:16-53
+ *   swec_expected_shard_size    calculateExpectedShardSize   weed/storage/disk_location_ec.go:428-448
+ *
+ * Threading: every entry point may be called concurrently from any OS thread (Go schedules
+ * gRPC handlers freely; the shell runs up to 10 volumes at once, weed/shell/common.go:11).
+ * Calls on ONE encoder handle serialise on its staging buffers; use one handle per goroutine
+ * (as the reference does: one reedsolomon.Encoder per file) for parallelism.
+ * Ownership: the caller owns every buffer; nothing is retained after a call returns.
+ */
+#ifndef SWEC_H
+#define SWEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWEC_MAX_SHARDS 32 /* MaxShardCount, ec_encoder.go:23 */
+
+typedef enum swec_status {
+    SWEC_OK = 0,
+    SWEC_ERR_INVALID_ARG = -1,     /* bad shard counts, NULL pointers, mismatched sizes        */
+    SWEC_ERR_TOO_FEW_SHARDS = -2,  /* fewer than data_shards present (ErrTooFewShards)          */
+    SWEC_ERR_CUDA = -3,            /* a CUDA call failed; swec_last_error() has the detail      */
+    SWEC_ERR_IO = -4,              /* open/read/write failed; errno text in swec_last_error()   */
+    SWEC_ERR_NOMEM = -5,
+    SWEC_ERR_SHARD_SIZE = -6,      /* shard files of unequal length ("ec shard size expected…") */
+    SWEC_ERR_NO_DEVICE = -7,       /* no usable CUDA device — there is NO CPU fallback          */
+    SWEC_ERR_JIT = -8              /* run-time kernel specialisation failed                     */
+} swec_status;
+
+typedef struct swec_encoder swec_encoder;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char *swec_version(void);
+const char *swec_strerror(int status);
+const char *swec_last_error(void);            /* thread-local detail of the last failure        */
+int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the driver is absent   */
+uint64_t swec_kernel_launches(void);          /* kernels this process has launched (all devices) */
+
+/* ---- encoder = reedsolomon.New(dataShards, parityShards) ----------------------------------- */
+/* device < 0: host-side object only (matrix queries); compute calls then fail with NO_DEVICE.  */
+int swec_encoder_new(int data_shards, int parity_shards, int device, swec_encoder **out);
+void swec_encoder_free(swec_encoder *enc);
+/* (k+m)×k generator matrix, row-major: identity on top, parity rows below.                     */
+int swec_encoder_matrix(const swec_encoder *enc, uint8_t *out);
+/* The fused matrix Reconstruct would apply for a presence mask: inputs[k] (shard ids read),
+ * outputs[*n_outputs] (shard ids produced), rows[*n_outputs * k].                              */
+int swec_reconstruct_matrix(const swec_encoder *enc, const uint8_t *present, int data_only,
+                            int *inputs, int *outputs, int *n_outputs, uint8_t *rows);
+
+/* ---- Encoder.Encode / Reconstruct / ReconstructData on HOST buffers ------------------------- */
+/* shards[0..k) are read, shards[k..k+m) are overwritten; all shard_len bytes, shard_len > 0.   */
+int swec_encode(swec_encoder *enc, uint8_t *const *shards, size_t shard_len);
+/* present[i] != 0 ⇔ shards[i] holds data.  Missing shards must point at shard_len writable
+ * bytes (the cgo shim allocates them, as klauspost does for nil slices).  data_only = 1 fills
+ * only indices < k (ReconstructData).  All present ⇒ no-op; fewer than k ⇒ TOO_FEW_SHARDS.     */
+int swec_reconstruct(swec_encoder *enc, uint8_t *const *shards, const uint8_t *present,
+                     size_t shard_len, int data_only);
+/* *ok = 1 iff the parity shards match the data shards.                                         */
+int swec_verify(swec_encoder *enc, uint8_t *const *shards, size_t shard_len, int *ok);
+
+/* ---- the same on DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the
+ *      encoder's own stream).  Buffers must stay valid until the stream reaches this point. --- */
+int swec_encode_device(swec_encoder *enc, const void *const *data, void *const *parity,
+                       size_t shard_len, void *stream);
+int swec_reconstruct_device(swec_encoder *enc, void *const *shards, const uint8_t *present,
+                            size_t shard_len, int data_only, void *stream);
+/* A whole volume image resident in HBM → parity shard images, following the two-tier striping
+ * of encodeDatFile (ec_encoder.go:280-321): rows of k large blocks while ≥ k*large bytes
+ * remain, then rows of k small blocks, the last one zero-padded.  parity[p] receives
+ * swec_expected_shard_size() bytes.  Data shards are views of the image and are not copied.    */
+int swec_encode_volume_device(swec_encoder *enc, const void *dat, int64_t dat_size,
+                              int64_t large_block, int64_t small_block, void *const *parity,
+                              void *stream);
+/* Gather data shard `shard_id` of the image into a contiguous shard buffer (what .ecNN holds).  */
+int swec_extract_data_shard_device(swec_encoder *enc, const void *dat, int64_t dat_size,
+                                   int64_t large_block, int64_t small_block, int shard_id,
+                                   void *shard_out, void *stream);
+int swec_stream_synchronize(swec_encoder *enc, void *stream);
+
+/* ---- file level: .dat → .ec00…, missing .ecNN ← the others, .ec00–.ec09 → .dat -------------- */
+/* WriteEcFiles(baseFileName): RS(10,4), 1 GiB / 1 MiB blocks.                                   */
+int swec_write_ec_files(const char *base_file_name, int device);
+/* generateEcFiles(base, bufferSize, large, small, ctx).  buffer_size only has to divide both
+ * block sizes (the reference Fatalf's otherwise); results do not depend on it.                  */
+int swec_generate_ec_files(const char *base_file_name, int64_t buffer_size, int64_t large_block,
+                           int64_t small_block, int data_shards, int parity_shards, int device);
+/* RebuildEcFiles(base, additionalDirs...).  data_shards = 0 ⇒ take the ratio from base.vif
+ * (ecShardConfig) when valid, else 10+4 (ec_encoder.go:76-95).  rebuilt[] (≥ SWEC_MAX_SHARDS
+ * entries) receives the generated shard ids.                                                    */
+int swec_rebuild_ec_files(const char *base_file_name, const char *const *additional_dirs,
+                          int n_additional_dirs, int data_shards, int parity_shards, int device,
+                          uint32_t *rebuilt, int *n_rebuilt);
+int swec_write_dat_file(const char *base_file_name, int64_t dat_file_size,
+                        const char *const *shard_file_names, int data_shards,
+                        int64_t large_block, int64_t small_block);
+
+/* ---- layout arithmetic (no GPU) ------------------------------------------------------------- */
+int64_t swec_expected_shard_size(int64_t dat_size, int data_shards, int64_t large_block,
+                                 int64_t small_block);
+typedef struct swec_interval {
+    int32_t block_index;
+    int32_t is_large_block;
+    int64_t inner_block_offset;
+    int64_t size;
+    int32_t large_block_rows_count;
+    int32_t reserved;
+} swec_interval;
+/* Returns the number of intervals written, or SWEC_ERR_INVALID_ARG if cap is too small.         */
+int swec_locate_data(int64_t large_block, int64_t small_block, int64_t shard_dat_size,
+                     int64_t offset, int64_t size, int data_shards, swec_interval *out, int cap);
+void swec_interval_to_shard(const swec_interval *iv, int64_t large_block, int64_t small_block,
+                            int data_shards, int *shard_id, int64_t *shard_offset);
+
+/* ---- pinned host memory for callers that stage their own buffers ---------------------------- */
+void *swec_alloc_pinned(size_t bytes);
+void swec_free_pinned(void *p);
+
+/* ---- measurement helpers (synthetic volumes, device digests) -------------------------------- */
+/* byte b of the stream = byte (b%8) of splitmix64(seed + (b/8 + 1)·0x9E3779B97F4A7C15).        */
+int swec_synth_fill_device(int device, void *dst, uint64_t byte_offset, size_t bytes,
+                           uint64_t seed, void *stream);
+/* 64-bit order-sensitive digest of a device buffer; synchronises `stream`.                      */
+int swec_digest_device(int device, const void *src, size_t bytes, uint64_t *digest, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWEC_H */

@@ -1,0 +1,99 @@
+// seaweedfs_b200/csrc/device_common.cuh — device-side building blocks shared by the ahead-of-time
+// kernels (kernels.cu) and the NVRTC-specialised kernels (jit.cc embeds this text verbatim, so it
+// must not include any header).  sm_100a only.
+//
+// Everything here computes, per byte column x,  out_p[x] = XOR_i M[p][i] ⊗ in_i[x]  over
+// GF(2^8)/0x11D — the arithmetic of reedsolomon.Encoder.Encode / Reconstruct
+// (weed/storage/erasure_coding/ec_encoder.go:265,360).
+#pragma once
+
+#include "apply_params.h"
+
+// ---- SWAR GF(2^8) primitives on four packed bytes ------------------------------------------
+// 3-input XOR = one LOP3 (immLut 0x96)
+__device__ __forceinline__ u32 swec_x3(u32 a, u32 b, u32 c) {
+    u32 r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+#define SWEC_X2(a, b) ((a) ^ (b))
+#define SWEC_X3(a, b, c) swec_x3((a), (b), (c))
+
+// Multiply each of the four bytes by 2 (the field generator) and add s:
+//   hi  = msb of every byte                       (LOP, alu pipe)
+//   m   = (hi >> 7) * 0x1D  = hi * (0x1D<<25) >> 32  (IMAD.HI, fma pipe) — the reduction term
+//   b2  = 2*(a - hi) = 2a - 2hi                   (two IMADs, fma pipe)   — bytes shifted left
+//   out = b2 ^ m ^ s                              (one LOP3, alu pipe)
+// Two alu-pipe and three fma-pipe instructions per step: the integer-ALU pipe is the scarce one.
+__device__ __forceinline__ u32 swec_xt1(u32 a, u32 s) {
+    const u32 hi = a & 0x80808080u;
+#if SWEC_XT_VARIANT == 1
+    // shift-based variant (all alu pipe except the multiply)
+    const u32 m = (hi >> 7) * 0x1du;
+    const u32 b2 = (a ^ hi) << 1;
+#else
+    u32 m, a2, b2;
+    asm("mul.hi.u32 %0, %1, 0x3a000000;" : "=r"(m) : "r"(hi));
+    asm("mul.lo.u32 %0, %1, 2;" : "=r"(a2) : "r"(a));
+    asm("mad.lo.u32 %0, %1, 0xfffffffe, %2;" : "=r"(b2) : "r"(hi), "r"(a2));
+#endif
+    return swec_x3(b2, m, s);
+}
+#define SWEC_XT1(a, s) swec_xt1((a), (s))
+#define SWEC_XT0(a) swec_xt1((a), 0u)
+
+// ---- streaming 16-byte global accesses (read-once / write-once data: keep it out of L1) -----
+__device__ __forceinline__ uint4 swec_ldg_stream(const u8* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void swec_stg_stream(u8* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// One thread = one 16-byte column slice of every stream per iteration: K coalesced LDG.128,
+// four independent 32-bit Horner evaluations (ILP), R coalesced STG.128.
+template <class Combiner, bool BLOCKED>
+__device__ __forceinline__ void swec_horner_body(const SwecApplyParams& p) {
+    constexpr int K = Combiner::K, R = Combiner::R;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < p.nvec; v += stride) {
+        const u64 off = v << 4;
+        u64 ioff = off;
+        if (BLOCKED) {
+            const u64 row = p.block_shift >= 0 ? (v >> p.block_shift) : (v / p.block_vecs);
+            ioff += row * p.row_extra;
+        }
+        uint4 d[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) d[i] = swec_ldg_stream(p.in[i] + ioff);
+        uint4 o[R];
+        u32 x[K], y[R];
+#pragma unroll
+        for (int i = 0; i < K; i++) x[i] = d[i].x;
+        Combiner::combine(x, y);
+#pragma unroll
+        for (int r = 0; r < R; r++) o[r].x = y[r];
+#pragma unroll
+        for (int i = 0; i < K; i++) x[i] = d[i].y;
+        Combiner::combine(x, y);
+#pragma unroll
+        for (int r = 0; r < R; r++) o[r].y = y[r];
+#pragma unroll
+        for (int i = 0; i < K; i++) x[i] = d[i].z;
+        Combiner::combine(x, y);
+#pragma unroll
+        for (int r = 0; r < R; r++) o[r].z = y[r];
+#pragma unroll
+        for (int i = 0; i < K; i++) x[i] = d[i].w;
+        Combiner::combine(x, y);
+#pragma unroll
+        for (int r = 0; r < R; r++) o[r].w = y[r];
+#pragma unroll
+        for (int r = 0; r < R; r++) swec_stg_stream(p.out[r] + off, o[r]);
+    }
+}

@@ -1,0 +1,563 @@
+// seaweedfs_b200/csrc/ec_files.cc — file-level entry points: the B200 twins of
+//   generateEcFiles / encodeDatFile / encodeData / encodeDataOneBatch
+//       (weed/storage/erasure_coding/ec_encoder.go:110-128, 202-222, 248-278, 280-321)
+//   generateMissingEcFiles / rebuildEcFiles / findShardFile      (ec_encoder.go:131-200, 323-377)
+//   WriteDatFile                                                (ec_decoder.go:176-223)
+// Same files, same bytes, same error points; different schedule.  The reference runs
+// read → Encode → write serially in 256 KiB batches on one goroutine.  Here a reader stages multi-MiB
+// stripes into pinned slots, the GPU turns each slot round on its own stream (H2D, kernel, D2H)
+// and a writer thread drains finished slots with pwrite at explicit shard offsets, so disk reads,
+// PCIe, the kernel and disk writes all overlap.  Batch size is result-neutral (the code is
+// column-wise), so buffer_size is only validated the way the reference does.
+#include <errno.h>
+#include <fcntl.h>
+#include <libgen.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <thread>
+
+#include "engine.h"
+
+namespace swec {
+namespace {
+
+size_t env_sz(const char* name, size_t dflt) {
+    const char* e = getenv(name);
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? size_t(v) : dflt;
+}
+
+int io_fail(const std::string& what) { return fail(SWEC_ERR_IO, what + ": " + strerror(errno)); }
+
+std::string shard_ext(int idx) {  // ToExt, ec_encoder.go:106-108
+    char b[16];
+    snprintf(b, sizeof b, ".ec%02d", idx);
+    return b;
+}
+
+struct FdSet {
+    std::vector<int> fds;
+    ~FdSet() {
+        for (int fd : fds)
+            if (fd >= 0) close(fd);
+    }
+};
+
+struct ReadOp { int stream, fd; int64_t off; };            // fill stream `stream` of the slot from fd@off
+struct WriteOp { int stream, fd; int64_t off; };           // drain stream `stream` of the slot to fd@off
+struct Item {
+    size_t len = 0;
+    std::vector<ReadOp> reads;
+    std::vector<WriteOp> writes;
+};
+
+struct Slot {
+    uint8_t* host = nullptr;
+    uint8_t* dev = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    Item item;
+};
+
+// K input streams + R computed streams per slot, pitch = chunk bytes.
+class FilePipeline {
+  public:
+    FilePipeline(swec_encoder* enc, const Matrix& rows, size_t chunk) : enc_(enc), rows_(rows), chunk_(chunk) {}
+    ~FilePipeline() { shutdown(); }
+
+    int start() {
+        int rc = enc_->ensure_device();
+        if (rc) return rc;
+        const size_t nslots = env_sz("SWEC_STAGE_SLOTS", 3);
+        const size_t streams = size_t(rows_.cols + rows_.rows);
+        slots_.resize(nslots);
+        for (auto& s : slots_) {
+            SWEC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.host), streams * chunk_, cudaHostAllocDefault));
+            SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk_));
+            SWEC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            SWEC_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            free_.push_back(&s);
+        }
+        writer_ = std::thread([this] { writer_loop(); });
+        started_ = true;
+        return SWEC_OK;
+    }
+
+    // blocking: read the item's inputs, queue the GPU work, hand the slot to the writer
+    int submit(Item&& item) {
+        Slot* s = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return !free_.empty() || error_; });
+            if (error_) return error_;
+            s = free_.front();
+            free_.pop_front();
+        }
+        const int K = rows_.cols, R = rows_.rows;
+        const size_t len = item.len;
+        for (const ReadOp& r : item.reads) {
+            uint8_t* dst = s->host + size_t(r.stream) * chunk_;
+            size_t got = 0;
+            while (got < len) {
+                const ssize_t n = pread(r.fd, dst + got, len - got, off_t(r.off + int64_t(got)));
+                if (n < 0) {
+                    if (errno == EINTR) continue;
+                    return set_error(io_fail("pread"), s);
+                }
+                if (n == 0) break;  // EOF: the rest reads as zero (ec_encoder.go:258-262)
+                got += size_t(n);
+            }
+            if (got < len) memset(dst + got, 0, len - got);
+        }
+        if (cudaSetDevice(enc_->device) != cudaSuccess) return set_error(fail(SWEC_ERR_CUDA, "cudaSetDevice"), s);
+        cudaError_t e = cudaSuccess;
+        const uint8_t* din[SWEC_MAX_SHARDS];
+        uint8_t* dout[SWEC_MAX_SHARDS];
+        for (int i = 0; i < K; i++) din[i] = s->dev + size_t(i) * chunk_;
+        if (len == chunk_) {  // full slot: the K input streams are contiguous — one DMA
+            e = cudaMemcpyAsync(s->dev, s->host, size_t(K) * chunk_, cudaMemcpyHostToDevice, s->stream);
+        } else {
+            for (int i = 0; i < K && e == cudaSuccess; i++)
+                e = cudaMemcpyAsync(s->dev + size_t(i) * chunk_, s->host + size_t(i) * chunk_, len, cudaMemcpyHostToDevice, s->stream);
+        }
+        if (e != cudaSuccess) return set_error(cuda_fail(e, "H2D"), s);
+        for (int r = 0; r < R; r++) dout[r] = s->dev + size_t(K + r) * chunk_;
+        int rc;
+        {
+            std::lock_guard<std::mutex> lk(enc_->mu);
+            rc = enc_->apply(rows_, din, dout, len, Layout{}, s->stream);
+        }
+        if (rc) return set_error(rc, s);
+        if (len == chunk_) {
+            e = cudaMemcpyAsync(s->host + size_t(K) * chunk_, dout[0], size_t(R) * chunk_, cudaMemcpyDeviceToHost, s->stream);
+        } else {
+            for (int r = 0; r < R && e == cudaSuccess; r++)
+                e = cudaMemcpyAsync(s->host + size_t(K + r) * chunk_, dout[r], len, cudaMemcpyDeviceToHost, s->stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(s->done, s->stream);
+        if (e != cudaSuccess) return set_error(cuda_fail(e, "D2H"), s);
+        s->item = std::move(item);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            inflight_.push_back(s);
+        }
+        cv_.notify_all();
+        return SWEC_OK;
+    }
+
+    // wait for everything queued so far; returns the first error
+    int finish() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return (inflight_.empty() && free_.size() == slots_.size()) || error_; });
+        return error_;
+    }
+
+    void shutdown() {
+        if (!started_) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        if (writer_.joinable()) writer_.join();
+        cudaSetDevice(enc_->device);
+        for (auto& s : slots_) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.host) cudaFreeHost(s.host);
+            if (s.dev) cudaFree(s.dev);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        slots_.clear();
+        started_ = false;
+    }
+
+  private:
+    int set_error(int rc, Slot* s) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!error_) {
+            error_ = rc;
+            error_msg_ = last_error();
+        }
+        if (s) free_.push_back(s);
+        cv_.notify_all();
+        return rc;
+    }
+
+    void writer_loop() {
+        cudaSetDevice(enc_->device);
+        for (;;) {
+            Slot* s = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return !inflight_.empty() || stop_; });
+                if (inflight_.empty()) return;
+                s = inflight_.front();
+            }
+            int rc = SWEC_OK;
+            if (cudaEventSynchronize(s->done) != cudaSuccess) rc = fail(SWEC_ERR_CUDA, "cudaEventSynchronize failed in the shard writer");
+            for (const WriteOp& w : s->item.writes) {
+                if (rc) break;
+                const uint8_t* src = s->host + size_t(w.stream) * chunk_;
+                size_t put = 0;
+                while (put < s->item.len) {
+                    const ssize_t n = pwrite(w.fd, src + put, s->item.len - put, off_t(w.off + int64_t(put)));
+                    if (n < 0) {
+                        if (errno == EINTR) continue;
+                        rc = io_fail("pwrite");
+                        break;
+                    }
+                    put += size_t(n);
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                inflight_.pop_front();
+                free_.push_back(s);
+                if (rc && !error_) {
+                    error_ = rc;
+                    error_msg_ = last_error();
+                }
+            }
+            cv_.notify_all();
+        }
+    }
+
+    swec_encoder* enc_;
+    Matrix rows_;
+    size_t chunk_;
+    std::vector<Slot> slots_;
+    std::deque<Slot*> free_, inflight_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::thread writer_;
+    int error_ = 0;
+    std::string error_msg_;
+    bool stop_ = false, started_ = false;
+
+  public:
+    const std::string& error_message() const { return error_msg_; }
+};
+
+// .vif is protobuf-JSON (weed/storage/volume_info/volume_info.go:73-95); we only need
+// ecShardConfig.{dataShards,parityShards} (weed/pb/volume_server.proto:561-577).
+bool read_vif_ratio(const std::string& path, int* ds, int* ps) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::string txt;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) txt.append(buf, n);
+    fclose(f);
+    const size_t cfg = txt.find("\"ecShardConfig\"");
+    if (cfg == std::string::npos) return false;
+    auto number_after = [&](const char* key, int* out) {
+        const size_t p = txt.find(key, cfg);
+        if (p == std::string::npos) return false;
+        size_t q = txt.find(':', p);
+        if (q == std::string::npos) return false;
+        q++;
+        while (q < txt.size() && (txt[q] == ' ' || txt[q] == '"' || txt[q] == '\t' || txt[q] == '\n')) q++;
+        *out = atoi(txt.c_str() + q);
+        return true;
+    };
+    int a = 0, b = 0;
+    if (!number_after("\"dataShards\"", &a) || !number_after("\"parityShards\"", &b)) return false;
+    *ds = a;
+    *ps = b;
+    return true;
+}
+
+bool file_exists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && !S_ISDIR(st.st_mode);
+}
+
+}  // namespace
+}  // namespace swec
+
+using namespace swec;
+
+extern "C" {
+
+int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large, int64_t small, int k, int m,
+                           int device) {
+    if (!base) return fail(SWEC_ERR_INVALID_ARG, "base_file_name is NULL");
+    // encodeData: "unexpected zero buffer size" / "unexpected block size %d buffer size %d" (ec_encoder.go:204-212)
+    if (buffer_size <= 0 || large <= 0 || small <= 0 || large % buffer_size || small % buffer_size)
+        return fail(SWEC_ERR_INVALID_ARG, "block sizes must be positive multiples of buffer_size");
+    swec_encoder* enc = nullptr;
+    int rc = swec_encoder_new(k, m, device, &enc);
+    if (rc) return rc;
+    std::unique_ptr<swec_encoder, void (*)(swec_encoder*)> guard(enc, swec_encoder_free);
+
+    const std::string b(base);
+    FdSet fds;
+    const int dat = open((b + ".dat").c_str(), O_RDONLY);
+    if (dat < 0) return io_fail("failed to open dat file " + b + ".dat");
+    fds.fds.push_back(dat);
+    struct stat st;
+    if (fstat(dat, &st) != 0) return io_fail("failed to stat dat file");
+    const int total = k + m;
+    std::vector<int> outs(static_cast<size_t>(total), -1);
+    for (int i = 0; i < total; i++) {  // openEcFiles, ec_encoder.go:224-238
+        const int fd = open((b + shard_ext(i)).c_str(), O_TRUNC | O_CREAT | O_WRONLY, 0644);
+        if (fd < 0) return io_fail("failed to open file " + b + shard_ext(i));
+        fds.fds.push_back(fd);
+        outs[size_t(i)] = fd;
+    }
+
+    Matrix rows(m, k);
+    memcpy(rows.v.data(), enc->gen.row(k), rows.v.size());
+    const int64_t max_chunk = int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20));
+    const size_t chunk = size_t(std::min<int64_t>(max_chunk, std::max(large, small)) + 255) & ~size_t(255);
+    FilePipeline pipe(enc, rows, chunk);
+    if ((rc = pipe.start())) return rc;
+
+    int64_t remaining = st.st_size, processed = 0, shard_off = 0;
+    const int64_t large_row = large * k, small_row = small * k;
+    auto encode_row = [&](int64_t block) -> int {  // encodeData: one row of k blocks
+        for (int64_t o = 0; o < block; o += int64_t(chunk)) {
+            Item it;
+            it.len = size_t(std::min<int64_t>(int64_t(chunk), block - o));
+            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + block * i + o});
+            for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off + o});
+            const int r = pipe.submit(std::move(it));
+            if (r) return r;
+        }
+        shard_off += block;
+        return SWEC_OK;
+    };
+    while (rc == SWEC_OK && remaining >= large_row) {  // ec_encoder.go:304-311
+        rc = encode_row(large);
+        remaining -= large_row;
+        processed += large_row;
+    }
+    while (rc == SWEC_OK && remaining > 0) {  // ec_encoder.go:312-319
+        rc = encode_row(small);
+        remaining -= small_row;
+        processed += small_row;
+    }
+    const int rc2 = pipe.finish();
+    if (rc == SWEC_OK) rc = rc2;
+    const std::string msg = pipe.error_message();
+    pipe.shutdown();
+    if (rc && !msg.empty()) set_last_error(msg);
+    return rc;
+}
+
+int swec_write_ec_files(const char* base, int device) {
+    // WriteEcFilesWithContext: 256 KiB buffers, 1 GiB / 1 MiB blocks, 10+4 (ec_encoder.go:61-69)
+    return swec_generate_ec_files(base, 256 * 1024, int64_t(1) << 30, int64_t(1) << 20, 10, 4, device);
+}
+
+int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, int k, int m, int device,
+                          uint32_t* rebuilt, int* n_rebuilt) {
+    if (!base || !rebuilt || !n_rebuilt || (ndirs > 0 && !dirs)) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    *n_rebuilt = 0;
+    const std::string b(base);
+    if (k == 0) {  // RebuildEcFiles: ratio from .vif when valid, else default (ec_encoder.go:76-95)
+        int ds = 0, ps = 0;
+        if (read_vif_ratio(b + ".vif", &ds, &ps) && ds > 0 && ps > 0 && ds + ps <= SWEC_MAX_SHARDS) {
+            k = ds;
+            m = ps;
+        } else {
+            k = 10;
+            m = 4;
+        }
+    }
+    swec_encoder* enc = nullptr;
+    int rc = swec_encoder_new(k, m, device, &enc);
+    if (rc) return rc;
+    std::unique_ptr<swec_encoder, void (*)(swec_encoder*)> guard(enc, swec_encoder_free);
+    const int total = k + m;
+
+    // pass 1: which shards exist (base dir first, then additionalDirs) — ec_encoder.go:131-169
+    std::string base_copy(b);
+    const std::string base_name = basename(&base_copy[0]);
+    FdSet fds;
+    std::vector<int> in(static_cast<size_t>(total), -1);
+    std::vector<uint8_t> present(static_cast<size_t>(total), 0);
+    int npresent = 0;
+    std::vector<uint32_t> missing;
+    for (int i = 0; i < total; i++) {
+        std::string path = b + shard_ext(i);
+        if (!file_exists(path)) {
+            path.clear();
+            for (int d = 0; d < ndirs; d++) {
+                const std::string cand = std::string(dirs[d]) + "/" + base_name + shard_ext(i);
+                if (file_exists(cand)) {
+                    path = cand;
+                    break;
+                }
+            }
+        }
+        if (path.empty()) {
+            missing.push_back(uint32_t(i));
+            continue;
+        }
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return io_fail("open " + path);
+        fds.fds.push_back(fd);
+        in[size_t(i)] = fd;
+        present[size_t(i)] = 1;
+        npresent++;
+    }
+    if (npresent < k)  // before any output file exists — ec_encoder.go:172-175
+        return fail(SWEC_ERR_TOO_FEW_SHARDS, "not enough shards to rebuild " + b + ": found " + std::to_string(npresent) +
+                                                 " shards, need at least " + std::to_string(k));
+    for (uint32_t id : missing) rebuilt[(*n_rebuilt)++] = id;
+    if (missing.empty()) return SWEC_OK;
+
+    // pass 2: create the outputs — ec_encoder.go:182-193
+    std::vector<int> out(static_cast<size_t>(total), -1);
+    for (uint32_t id : missing) {
+        const int fd = open((b + shard_ext(int(id))).c_str(), O_TRUNC | O_WRONLY | O_CREAT, 0644);
+        if (fd < 0) return io_fail("create " + b + shard_ext(int(id)));
+        fds.fds.push_back(fd);
+        out[id] = fd;
+    }
+
+    // rebuildEcFiles (ec_encoder.go:323-377): every present shard must have the same length; the
+    // reference steps in 1 MiB reads and fails at the first short, unequal one.
+    int64_t size = -1;
+    for (int i = 0; i < total; i++) {
+        if (!present[size_t(i)]) continue;
+        struct stat st;
+        if (fstat(in[size_t(i)], &st) != 0) return io_fail("fstat shard");
+        if (size < 0) size = st.st_size;
+        else if (size != st.st_size)
+            return fail(SWEC_ERR_SHARD_SIZE, "ec shard size expected " + std::to_string(size) + " actual " + std::to_string(st.st_size));
+    }
+    const int64_t mib = int64_t(1) << 20;
+    // quirk kept: a length above 1 MiB that is not a multiple of 1 MiB errors on the last read
+    const bool ragged = size > mib && size % mib != 0;
+    const int64_t todo = ragged ? size / mib * mib : size;
+
+    std::vector<int> ins, outs_idx;
+    Matrix fused;
+    if (!rs_reconstruct_plan(enc->gen, k, present.data(), false, &ins, &outs_idx, &fused))
+        return fail(SWEC_ERR_TOO_FEW_SHARDS, "not enough shards");
+    const size_t chunk = std::max<size_t>(256, (size_t(std::min<int64_t>(int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20)), std::max<int64_t>(todo, 1))) + 255) & ~size_t(255));
+    FilePipeline pipe(enc, fused, chunk);
+    if ((rc = pipe.start())) return rc;
+    for (int64_t o = 0; rc == SWEC_OK && o < todo; o += int64_t(chunk)) {
+        Item it;
+        it.len = size_t(std::min<int64_t>(int64_t(chunk), todo - o));
+        for (int i = 0; i < k; i++) it.reads.push_back({i, in[size_t(ins[size_t(i)])], o});
+        for (size_t r = 0; r < outs_idx.size(); r++) it.writes.push_back({k + int(r), out[size_t(outs_idx[r])], o});
+        rc = pipe.submit(std::move(it));
+    }
+    const int rc2 = pipe.finish();
+    if (rc == SWEC_OK) rc = rc2;
+    const std::string msg = pipe.error_message();
+    pipe.shutdown();
+    if (rc) {
+        if (!msg.empty()) set_last_error(msg);
+        return rc;
+    }
+    if (ragged) return fail(SWEC_ERR_SHARD_SIZE, "ec shard size expected 1048576 actual " + std::to_string(size % mib));
+    return SWEC_OK;
+}
+
+int swec_write_dat_file(const char* base, int64_t dat_size, const char* const* shard_names, int k, int64_t large,
+                        int64_t small) {
+    if (!base || !shard_names || k <= 0 || k > SWEC_MAX_SHARDS || large <= 0 || small <= 0 || dat_size < 0)
+        return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    FdSet fds;
+    const int dat = open((std::string(base) + ".dat").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (dat < 0) return io_fail("cannot write volume .dat");
+    fds.fds.push_back(dat);
+    std::vector<int> in;
+    for (int i = 0; i < k; i++) {
+        const int fd = open(shard_names[i], O_RDONLY);
+        if (fd < 0) return io_fail(std::string("open ") + shard_names[i]);
+        fds.fds.push_back(fd);
+        in.push_back(fd);
+    }
+    std::vector<uint8_t> buf(size_t(4) << 20);
+    std::vector<int64_t> pos(static_cast<size_t>(k), 0);
+    int64_t out = 0;
+    auto copy = [&](int shard, int64_t n) -> int {  // io.CopyN
+        while (n > 0) {
+            const size_t want = size_t(std::min<int64_t>(n, int64_t(buf.size())));
+            const ssize_t got = pread(in[size_t(shard)], buf.data(), want, off_t(pos[size_t(shard)]));
+            if (got <= 0) return fail(SWEC_ERR_IO, "short read copying shard " + std::to_string(shard));
+            if (pwrite(dat, buf.data(), size_t(got), off_t(out)) != got) return io_fail("write .dat");
+            pos[size_t(shard)] += got;
+            out += got;
+            n -= got;
+        }
+        return SWEC_OK;
+    };
+    int64_t remaining = dat_size;
+    while (remaining >= int64_t(k) * large)  // ec_decoder.go:200-208
+        for (int s = 0; s < k; s++) {
+            const int rc = copy(s, large);
+            if (rc) return rc;
+            remaining -= large;
+        }
+    while (remaining > 0)  // ec_decoder.go:210-219
+        for (int s = 0; s < k; s++) {
+            const int64_t n = std::min(remaining, small);
+            const int rc = copy(s, n);
+            if (rc) return rc;
+            remaining -= n;
+        }
+    return SWEC_OK;
+}
+
+// ---- layout arithmetic -----------------------------------------------------------------------
+
+int swec_locate_data(int64_t large, int64_t small, int64_t shard_dat_size, int64_t offset, int64_t size, int k,
+                     swec_interval* out, int cap) {
+    if (large <= 0 || small <= 0 || k <= 0 || !out) return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    const int64_t nlarge_rows = shard_dat_size / large;  // ec_locate.go:67
+    const int64_t large_area = nlarge_rows * large * k;
+    bool is_large = offset < large_area;
+    const int64_t rel = is_large ? offset : offset - large_area;
+    const int64_t blk = is_large ? large : small;
+    int64_t block_index = rel / blk, inner = rel % blk;
+    int n = 0;
+    while (size > 0) {
+        const int64_t room = (is_large ? large : small) - inner;
+        if (room > 0) {
+            if (n >= cap) return fail(SWEC_ERR_INVALID_ARG, "interval buffer too small");
+            swec_interval& iv = out[n++];
+            iv.block_index = int32_t(block_index);
+            iv.is_large_block = is_large ? 1 : 0;
+            iv.inner_block_offset = inner;
+            iv.large_block_rows_count = int32_t(nlarge_rows);
+            iv.reserved = 0;
+            iv.size = std::min(size, room);
+            size -= iv.size;
+            if (size == 0) break;
+        }
+        // moveToNextBlock (ec_locate.go:55-63): the block after the last large one is small block 0
+        block_index++;
+        if (is_large && block_index == nlarge_rows * k) {
+            is_large = false;
+            block_index = 0;
+        }
+        inner = 0;
+    }
+    return n;
+}
+
+void swec_interval_to_shard(const swec_interval* iv, int64_t large, int64_t small, int k, int* shard_id,
+                            int64_t* shard_offset) {
+    const int64_t row = iv->block_index / k;  // ec_locate.go:87-98
+    int64_t off = iv->inner_block_offset;
+    off += iv->is_large_block ? row * large : int64_t(iv->large_block_rows_count) * large + row * small;
+    if (shard_id) *shard_id = iv->block_index % k;
+    if (shard_offset) *shard_offset = off;
+}
+
+}  // extern "C"

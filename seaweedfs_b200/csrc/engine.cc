@@ -1,0 +1,661 @@
+// seaweedfs_b200/csrc/engine.cc — encoder object, matrix→kernel dispatch, host staging pipeline.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace swec {
+
+// ------------------------------------------------------------------ errors
+
+static thread_local std::string t_last_error;
+
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+const char* last_error() { return t_last_error.c_str(); }
+
+int fail(int status, const std::string& msg) {
+    set_last_error(msg);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    const bool nodev = e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice;
+    set_last_error(std::string(what) + ": " + cudaGetErrorName(e) + " — " + cudaGetErrorString(e));
+    return nodev ? SWEC_ERR_NO_DEVICE : SWEC_ERR_CUDA;
+}
+
+static size_t env_size(const char* name, size_t dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long long v = atoll(e);
+    return v > 0 ? size_t(v) : dflt;
+}
+
+// ------------------------------------------------------------------ encoder lifetime
+
+swec_encoder_impl::~swec_encoder_impl() {
+    if (device < 0) return;
+    if (cudaSetDevice(device) != cudaSuccess) return;
+    for (auto& kv : tables) {
+        cudaFree(kv.second.compact);
+        cudaFree(kv.second.replicated);
+    }
+    for (auto& s : slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.host) cudaFreeHost(s.host);
+        if (s.dev) cudaFree(s.dev);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (tail_scratch) cudaFree(tail_scratch);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int swec_encoder_impl::ensure_device() {
+    if (device < 0) return fail(SWEC_ERR_NO_DEVICE, "encoder was created without a device (device < 0); no CPU fallback exists");
+    SWEC_CUDA(cudaSetDevice(device));
+    if (!stream) SWEC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return SWEC_OK;
+}
+
+int swec_encoder_impl::ensure_slots(size_t chunk) {
+    if (!slots.empty() && slot_chunk >= chunk) return SWEC_OK;
+    for (auto& s : slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.host) cudaFreeHost(s.host);
+        if (s.dev) cudaFree(s.dev);
+        s.host = s.dev = nullptr;
+    }
+    const size_t nslots = env_size("SWEC_STAGE_SLOTS", 3);
+    slots.resize(nslots);
+    const size_t streams = size_t(k) + 2 * size_t(m);
+    for (auto& s : slots) {
+        SWEC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.host), streams * chunk, cudaHostAllocDefault));
+        SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk));
+        if (!s.stream) SWEC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.done) SWEC_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        s.busy = false;
+    }
+    slot_chunk = chunk;
+    return SWEC_OK;
+}
+
+// ------------------------------------------------------------------ tables
+
+static std::vector<uint8_t> matrix_key(const Matrix& rows) {
+    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols)};
+    key.insert(key.end(), rows.v.begin(), rows.v.end());
+    return key;
+}
+
+int swec_encoder_impl::get_tables(const Matrix& rows, DeviceTables* out, cudaStream_t s) {
+    const auto key = matrix_key(rows);
+    auto it = tables.find(key);
+    if (it != tables.end()) {
+        *out = it->second;
+        return SWEC_OK;
+    }
+    const GF& gf = GF::get();
+    const int K = rows.cols, R = rows.rows;
+    std::vector<u32> compact(size_t(K) * 32), repl(size_t(K) * 32 * 32);
+    for (int i = 0; i < K; i++)
+        for (int h = 0; h < 2; h++)
+            for (int v = 0; v < 16; v++) {
+                u32 w = 0;
+                for (int r = 0; r < R; r++) w |= u32(gf.mul[rows.at(r, i)][uint8_t(v << (4 * h))]) << (8 * r);
+                const size_t e = size_t(i) * 32 + size_t(h) * 16 + size_t(v);
+                compact[e] = w;
+                for (int lane = 0; lane < 32; lane++) repl[e * 32 + size_t(lane)] = w;
+            }
+    DeviceTables t;
+    SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.compact), compact.size() * 4));
+    SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.replicated), repl.size() * 4));
+    // synchronous copies from pageable memory: the vectors die at return
+    SWEC_CUDA(cudaMemcpyAsync(t.compact, compact.data(), compact.size() * 4, cudaMemcpyHostToDevice, s));
+    SWEC_CUDA(cudaMemcpyAsync(t.replicated, repl.data(), repl.size() * 4, cudaMemcpyHostToDevice, s));
+    SWEC_CUDA(cudaStreamSynchronize(s));
+    tables[key] = t;
+    *out = t;
+    return SWEC_OK;
+}
+
+// ------------------------------------------------------------------ matrix → kernel dispatch
+
+static bool is_rs10x4_parity(const swec_encoder_impl& e, const Matrix& rows) {
+    if (!e.rs10x4 || rows.rows != 4 || rows.cols != 10) return false;
+    for (int r = 0; r < 4; r++)
+        if (memcmp(rows.row(r), e.gen.row(10 + r), 10) != 0) return false;
+    return true;
+}
+
+static int ilog2_exact(uint64_t v) {
+    if (!v || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((v >> s) != 1) s++;
+    return s;
+}
+
+int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8_t* const* out, size_t n,
+                             const Layout& layout, cudaStream_t s) {
+    const int R = rows.rows, K = rows.cols;
+    if (R == 0 || n == 0) return SWEC_OK;
+    if (K > SWEC_MAX_INPUTS) return fail(SWEC_ERR_INVALID_ARG, "too many input shards");
+
+    uintptr_t align = 0;
+    for (int i = 0; i < K; i++) align |= reinterpret_cast<uintptr_t>(in[i]);
+    for (int r = 0; r < R; r++) align |= reinterpret_cast<uintptr_t>(out[r]);
+    if (layout.blocked) align |= layout.block_bytes;
+    const bool aligned = (align & 15) == 0;
+    const size_t nvec = aligned ? n / 16 : 0;
+    const size_t tail_off = nvec * 16, tail = n - tail_off;
+    if (layout.blocked && (!aligned || tail))
+        return fail(SWEC_ERR_INVALID_ARG, "blocked layout needs 16-byte aligned blocks");
+
+    auto fill = [&](SwecApplyParams& p, int r0, int rn, size_t off) {
+        memset(&p, 0, sizeof p);
+        for (int i = 0; i < K; i++) p.in[i] = in[i] + off;
+        for (int r = 0; r < rn; r++) p.out[r] = out[r0 + r] + off;
+        p.nvec = nvec;
+        p.block_shift = -1;
+        if (layout.blocked) {
+            p.block_vecs = layout.block_bytes / 16;
+            p.block_shift = ilog2_exact(p.block_vecs);
+            p.row_extra = uint64_t(K - 1) * layout.block_bytes;
+        }
+    };
+
+    if (nvec) {
+        SwecApplyParams p;
+        if (is_rs10x4_parity(*this, rows)) {
+            fill(p, 0, R, 0);
+            SWEC_CUDA(launch_rs10x4_encode(p, layout.blocked, s));
+        } else {
+            // specialised (NVRTC) Horner kernel when the stream is long enough to pay for the
+            // compile, or the kernel is already cached; otherwise shared-memory tables.
+            static const size_t jit_min = env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20);
+            std::shared_ptr<JitKernel> jk;
+            const bool want_jit = R <= SWEC_MAX_OUTPUTS && jit_available() &&
+                                  (jit.count(matrix_key(rows)) || size_t(K) * n >= jit_min);
+            if (want_jit) {
+                const int rc = jit_get(this, rows, &jk);
+                if (rc != SWEC_OK && getenv("SWEC_JIT_STRICT")) return rc;
+            }
+            if (jk) {
+                fill(p, 0, R, 0);
+                SWEC_CUDA(jit_launch(*jk, p, layout.blocked, s));
+            } else {
+                if (layout.blocked) return fail(SWEC_ERR_INVALID_ARG, "blocked layout needs a specialised kernel");
+                for (int r0 = 0; r0 < R; r0 += 4) {
+                    const int rn = std::min(4, R - r0);
+                    Matrix sub(rn, K);
+                    for (int r = 0; r < rn; r++) memcpy(&sub.v[size_t(r) * K], rows.row(r0 + r), size_t(K));
+                    DeviceTables t;
+                    int rc = get_tables(sub, &t, s);
+                    if (rc) return rc;
+                    fill(p, r0, rn, 0);
+                    SWEC_CUDA(launch_table_apply(p, t.replicated, K, rn, s));
+                }
+            }
+        }
+    }
+    if (tail) {
+        for (int r0 = 0; r0 < R; r0 += 4) {
+            const int rn = std::min(4, R - r0);
+            Matrix sub(rn, K);
+            for (int r = 0; r < rn; r++) memcpy(&sub.v[size_t(r) * K], rows.row(r0 + r), size_t(K));
+            DeviceTables t;
+            int rc = get_tables(sub, &t, s);
+            if (rc) return rc;
+            SwecApplyParams p;
+            fill(p, r0, rn, tail_off);
+            SWEC_CUDA(launch_bytes_apply(p, t.compact, K, rn, tail, s));
+        }
+    }
+    return SWEC_OK;
+}
+
+// ------------------------------------------------------------------ host staging pipeline
+// Chunks of every stream travel pinned-host → HBM → kernel → pinned-host on one of a few slots,
+// each with its own stream, so H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1
+// overlap.  Caller buffers that are already pinned (swec_alloc_pinned / cudaHostRegister) are
+// DMA'd directly; pageable ones bounce through the slot's pinned buffer.
+
+namespace {
+
+struct PendingCopy {
+    uint8_t* dst;
+    const uint8_t* src;
+    size_t len;
+};
+
+bool is_pinned_or_device(const void* p, bool* is_device) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        *is_device = false;
+        return false;
+    }
+    *is_device = a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    return a.type == cudaMemoryTypeHost || *is_device;
+}
+
+}  // namespace
+
+// check = nullptr: out[r] receive the results.  check != nullptr: out[r] are read and compared
+// with the computed rows; *check receives the number of mismatching 16-byte vectors.
+static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* const* in, uint8_t* const* out,
+                      size_t n, unsigned long long* check) {
+    const int K = rows.cols, R = rows.rows;
+    if (R == 0 || n == 0) return SWEC_OK;
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+
+    std::vector<char> in_direct(static_cast<size_t>(K), 0), out_direct(static_cast<size_t>(R), 0);
+    int ndev = 0;
+    for (int i = 0; i < K; i++) {
+        bool dev;
+        in_direct[size_t(i)] = is_pinned_or_device(in[i], &dev);
+        ndev += dev;
+    }
+    for (int r = 0; r < R; r++) {
+        bool dev;
+        out_direct[size_t(r)] = is_pinned_or_device(out[r], &dev);
+        ndev += dev;
+    }
+    if (ndev == K + R && !check) {  // everything already lives in HBM
+        rc = e->apply(rows, in, out, n, Layout{}, e->stream);
+        if (rc) return rc;
+        SWEC_CUDA(cudaStreamSynchronize(e->stream));
+        return SWEC_OK;
+    }
+
+    const size_t max_chunk = env_size("SWEC_STAGE_CHUNK", size_t(4) << 20);
+    const size_t chunk = std::min(max_chunk, (n + 255) & ~size_t(255));
+    rc = e->ensure_slots(chunk);
+    if (rc) return rc;
+    const size_t stride = e->slot_chunk;  // per-stream pitch inside a slot (>= chunk)
+
+    unsigned long long* dev_bad = nullptr;
+    if (check) {
+        SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev_bad), 8));
+        SWEC_CUDA(cudaMemset(dev_bad, 0, 8));
+    }
+
+    std::vector<std::vector<PendingCopy>> pending(e->slots.size());
+    auto finish = [&](size_t si) -> int {
+        StagingSlot& s = e->slots[si];
+        if (!s.busy) return SWEC_OK;
+        SWEC_CUDA(cudaEventSynchronize(s.done));
+        for (const PendingCopy& pc : pending[si]) memcpy(pc.dst, pc.src, pc.len);
+        pending[si].clear();
+        s.busy = false;
+        return SWEC_OK;
+    };
+
+    size_t ci = 0;
+    for (size_t off = 0; off < n; off += chunk, ci++) {
+        const size_t si = ci % e->slots.size();
+        StagingSlot& s = e->slots[si];
+        if ((rc = finish(si))) break;
+        const size_t len = std::min(chunk, n - off);
+        const uint8_t* din[SWEC_MAX_INPUTS];
+        uint8_t* dout[SWEC_MAX_SHARDS];
+        for (int i = 0; i < K; i++) {
+            uint8_t* d = s.dev + size_t(i) * stride;
+            din[i] = d;
+            const uint8_t* src = in[i] + off;
+            if (!in_direct[size_t(i)]) {
+                memcpy(s.host + size_t(i) * stride, src, len);
+                src = s.host + size_t(i) * stride;
+            }
+            SWEC_CUDA(cudaMemcpyAsync(d, src, len, cudaMemcpyDefault, s.stream));
+        }
+        for (int r = 0; r < R; r++) dout[r] = s.dev + size_t(K + r) * stride;
+        if ((rc = e->apply(rows, din, dout, len, Layout{}, s.stream))) break;
+        for (int r = 0; r < R; r++) {
+            if (check) {
+                // bring the caller's copy of this row next to the computed one and compare in HBM
+                uint8_t* theirs = s.dev + size_t(K + R + r) * stride;
+                const uint8_t* src = out[r] + off;
+                if (!out_direct[size_t(r)]) {
+                    memcpy(s.host + size_t(K + r) * stride, src, len);
+                    src = s.host + size_t(K + r) * stride;
+                }
+                SWEC_CUDA(cudaMemcpyAsync(theirs, src, len, cudaMemcpyDefault, s.stream));
+                SWEC_CUDA(launch_compare(dout[r], theirs, len, dev_bad, s.stream));
+            } else if (out_direct[size_t(r)]) {
+                SWEC_CUDA(cudaMemcpyAsync(out[r] + off, dout[r], len, cudaMemcpyDefault, s.stream));
+            } else {
+                uint8_t* bounce = s.host + size_t(K + r) * stride;
+                SWEC_CUDA(cudaMemcpyAsync(bounce, dout[r], len, cudaMemcpyDeviceToHost, s.stream));
+                pending[si].push_back({out[r] + off, bounce, len});
+            }
+        }
+        SWEC_CUDA(cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    for (size_t si = 0; si < e->slots.size(); si++) {
+        const int rc2 = finish(si);
+        if (!rc) rc = rc2;
+    }
+    if (check) {
+        if (!rc && cudaMemcpy(check, dev_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SWEC_ERR_CUDA;
+        cudaFree(dev_bad);
+    }
+    return rc;
+}
+
+}  // namespace swec
+
+// =================================================================== C ABI
+
+using namespace swec;
+
+extern "C" {
+
+const char* swec_version(void) { return "swec 0.1 (sm_100a)"; }
+
+const char* swec_strerror(int status) {
+    switch (status) {
+        case SWEC_OK: return "ok";
+        case SWEC_ERR_INVALID_ARG: return "invalid argument";
+        case SWEC_ERR_TOO_FEW_SHARDS: return "too few shards given";
+        case SWEC_ERR_CUDA: return "CUDA error";
+        case SWEC_ERR_IO: return "I/O error";
+        case SWEC_ERR_NOMEM: return "out of memory";
+        case SWEC_ERR_SHARD_SIZE: return "shard sizes do not match";
+        case SWEC_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case SWEC_ERR_JIT: return "run-time kernel specialisation failed";
+        default: return "unknown error";
+    }
+}
+
+const char* swec_last_error(void) { return last_error(); }
+
+int swec_device_count(int* count) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = e == cudaSuccess ? n : 0;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(e, "cudaGetDeviceCount") == SWEC_ERR_CUDA ? SWEC_ERR_NO_DEVICE : SWEC_ERR_NO_DEVICE;
+    }
+    return n > 0 ? SWEC_OK : fail(SWEC_ERR_NO_DEVICE, "no CUDA devices");
+}
+
+uint64_t swec_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int swec_encoder_new(int k, int m, int device, swec_encoder** out) {
+    if (!out) return fail(SWEC_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    // reedsolomon.New: ErrInvShardNum for non-positive counts; SeaweedFS caps the total at
+    // MaxShardCount (ec_encoder.go:23,81)
+    if (k <= 0 || m <= 0 || k + m > SWEC_MAX_SHARDS)
+        return fail(SWEC_ERR_INVALID_ARG, "need data_shards > 0, parity_shards > 0, total <= 32");
+    swec_encoder* e = new (std::nothrow) swec_encoder();
+    if (!e) return fail(SWEC_ERR_NOMEM, "out of memory");
+    e->k = k;
+    e->m = m;
+    e->device = device;
+    e->gen = rs_generator(k, m);
+    e->rs10x4 = (k == 10 && m == 4);
+    *out = e;
+    return SWEC_OK;
+}
+
+void swec_encoder_free(swec_encoder* e) { delete e; }
+
+int swec_encoder_matrix(const swec_encoder* e, uint8_t* out) {
+    if (!e || !out) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    memcpy(out, e->gen.v.data(), e->gen.v.size());
+    return SWEC_OK;
+}
+
+int swec_reconstruct_matrix(const swec_encoder* e, const uint8_t* present, int data_only, int* inputs,
+                            int* outputs, int* n_outputs, uint8_t* rows) {
+    if (!e || !present || !inputs || !outputs || !n_outputs || !rows) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::vector<int> in, outv;
+    Matrix fused;
+    if (!rs_reconstruct_plan(e->gen, e->k, present, data_only != 0, &in, &outv, &fused))
+        return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+    for (int i = 0; i < e->k; i++) inputs[i] = in[size_t(i)];
+    *n_outputs = int(outv.size());
+    for (size_t i = 0; i < outv.size(); i++) outputs[i] = outv[i];
+    if (!fused.v.empty()) memcpy(rows, fused.v.data(), fused.v.size());
+    return SWEC_OK;
+}
+
+static Matrix parity_rows(const swec_encoder* e) {
+    Matrix rows(e->m, e->k);
+    memcpy(rows.v.data(), e->gen.row(e->k), rows.v.size());
+    return rows;
+}
+
+int swec_encode(swec_encoder* e, uint8_t* const* shards, size_t n) {
+    if (!e || !shards) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    if (n == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0 (ErrShardNoData)");
+    for (int i = 0; i < e->k + e->m; i++)
+        if (!shards[i]) return fail(SWEC_ERR_INVALID_ARG, "NULL shard");
+    return apply_host(e, parity_rows(e), shards, shards + e->k, n, nullptr);
+}
+
+int swec_reconstruct(swec_encoder* e, uint8_t* const* shards, const uint8_t* present, size_t n, int data_only) {
+    if (!e || !shards || !present) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    int npresent = 0;
+    for (int i = 0; i < e->k + e->m; i++) npresent += present[i] ? 1 : 0;
+    if (npresent == e->k + e->m) return SWEC_OK;  // nothing to do
+    if (npresent < e->k) return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+    if (n == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0 (ErrShardNoData)");
+    std::vector<int> in, outv;
+    Matrix fused;
+    if (!rs_reconstruct_plan(e->gen, e->k, present, data_only != 0, &in, &outv, &fused))
+        return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+    if (outv.empty()) return SWEC_OK;
+    const uint8_t* ins[SWEC_MAX_SHARDS];
+    uint8_t* outs[SWEC_MAX_SHARDS];
+    for (size_t i = 0; i < in.size(); i++) ins[i] = shards[in[i]];
+    for (size_t i = 0; i < outv.size(); i++) {
+        outs[i] = shards[outv[i]];
+        if (!outs[i]) return fail(SWEC_ERR_INVALID_ARG, "missing shard has no buffer");
+    }
+    return apply_host(e, fused, ins, outs, n, nullptr);
+}
+
+int swec_verify(swec_encoder* e, uint8_t* const* shards, size_t n, int* ok) {
+    if (!e || !shards || !ok) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    if (n == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0");
+    unsigned long long bad = 0;
+    const int rc = apply_host(e, parity_rows(e), shards, shards + e->k, n, &bad);
+    *ok = rc == SWEC_OK && bad == 0;
+    return rc;
+}
+
+// ---- device-resident
+
+static cudaStream_t pick_stream(swec_encoder* e, void* stream) {
+    return stream ? static_cast<cudaStream_t>(stream) : e->stream;
+}
+
+int swec_encode_device(swec_encoder* e, const void* const* data, void* const* parity, size_t n, void* stream) {
+    if (!e || !data || !parity) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    return e->apply(parity_rows(e), reinterpret_cast<const uint8_t* const*>(data),
+                    reinterpret_cast<uint8_t* const*>(parity), n, Layout{}, pick_stream(e, stream));
+}
+
+int swec_reconstruct_device(swec_encoder* e, void* const* shards, const uint8_t* present, size_t n, int data_only,
+                            void* stream) {
+    if (!e || !shards || !present) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::vector<int> in, outv;
+    Matrix fused;
+    if (!rs_reconstruct_plan(e->gen, e->k, present, data_only != 0, &in, &outv, &fused))
+        return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+    if (outv.empty()) return SWEC_OK;
+    const uint8_t* ins[SWEC_MAX_SHARDS];
+    uint8_t* outs[SWEC_MAX_SHARDS];
+    for (size_t i = 0; i < in.size(); i++) ins[i] = static_cast<const uint8_t*>(shards[in[i]]);
+    for (size_t i = 0; i < outv.size(); i++) outs[i] = static_cast<uint8_t*>(shards[outv[i]]);
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    return e->apply(fused, ins, outs, n, Layout{}, pick_stream(e, stream));
+}
+
+int64_t swec_expected_shard_size(int64_t dat_size, int k, int64_t large, int64_t small) {
+    if (k <= 0 || large <= 0 || small <= 0 || dat_size < 0) return 0;
+    const int64_t large_row = large * k, small_row = small * k;
+    const int64_t nlarge = dat_size / large_row;
+    int64_t size = nlarge * large;
+    const int64_t rem = dat_size - nlarge * large_row;
+    if (rem > 0) size += ((rem + small_row - 1) / small_row) * small;
+    return size;
+}
+
+int swec_encode_volume_device(swec_encoder* e, const void* dat_v, int64_t dat_size, int64_t large, int64_t small,
+                              void* const* parity, void* stream) {
+    if (!e || !dat_v || !parity || dat_size < 0 || large <= 0 || small <= 0)
+        return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    const uint8_t* dat = static_cast<const uint8_t*>(dat_v);
+    const int k = e->k, m = e->m;
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    cudaStream_t s = pick_stream(e, stream);
+    const Matrix rows = parity_rows(e);
+    bool horner = is_rs10x4_parity(*e, rows);
+    if (!horner && e->m <= SWEC_MAX_OUTPUTS && jit_available()) {
+        std::shared_ptr<JitKernel> jk;
+        horner = jit_get(e, rows, &jk) == SWEC_OK;
+    }
+
+    // one region = `nrows` rows of k blocks of `block` bytes starting at `base`; parity offset `poff`
+    auto region = [&](const uint8_t* base, int64_t block, int64_t nrows, int64_t poff) -> int {
+        const uint8_t* ins[SWEC_MAX_SHARDS];
+        uint8_t* outs[SWEC_MAX_SHARDS];
+        const bool vec_ok = horner && block % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+        if (vec_ok || nrows == 1) {
+            for (int i = 0; i < k; i++) ins[i] = base + int64_t(i) * block;
+            for (int p = 0; p < m; p++) outs[p] = static_cast<uint8_t*>(parity[p]) + poff;
+            Layout lay;
+            lay.blocked = nrows > 1;
+            lay.block_bytes = uint64_t(block);
+            return e->apply(rows, ins, outs, size_t(nrows * block), lay, s);
+        }
+        for (int64_t r = 0; r < nrows; r++) {  // unaligned / table path: one flat launch per row
+            for (int i = 0; i < k; i++) ins[i] = base + (r * k + i) * block;
+            for (int p = 0; p < m; p++) outs[p] = static_cast<uint8_t*>(parity[p]) + poff + r * block;
+            const int rc2 = e->apply(rows, ins, outs, size_t(block), Layout{}, s);
+            if (rc2) return rc2;
+        }
+        return SWEC_OK;
+    };
+
+    const int64_t large_row = large * k, small_row = small * k;
+    const int64_t nlarge = dat_size / large_row;       // while remaining >= largeRowSize  (ec_encoder.go:304)
+    if (nlarge && (rc = region(dat, large, nlarge, 0))) return rc;
+    const int64_t rem = dat_size - nlarge * large_row;
+    if (rem > 0) {                                     // while remaining > 0             (ec_encoder.go:312)
+        const uint8_t* base = dat + nlarge * large_row;
+        const int64_t nfull = rem / small_row;
+        if (nfull && (rc = region(base, small, nfull, nlarge * large))) return rc;
+        const int64_t tail = rem - nfull * small_row;
+        if (tail > 0) {  // last row: bytes past EOF read as zero (ec_encoder.go:258-262)
+            uint8_t* scratch = nullptr;
+            SWEC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), size_t(small_row), s));
+            SWEC_CUDA(cudaMemsetAsync(scratch, 0, size_t(small_row), s));
+            SWEC_CUDA(cudaMemcpyAsync(scratch, base + nfull * small_row, size_t(tail), cudaMemcpyDeviceToDevice, s));
+            rc = region(scratch, small, 1, nlarge * large + nfull * small);
+            SWEC_CUDA(cudaFreeAsync(scratch, s));
+            if (rc) return rc;
+        }
+    }
+    return SWEC_OK;
+}
+
+int swec_extract_data_shard_device(swec_encoder* e, const void* dat_v, int64_t dat_size, int64_t large, int64_t small,
+                                   int shard_id, void* shard_out, void* stream) {
+    if (!e || !dat_v || !shard_out || shard_id < 0 || shard_id >= e->k || large <= 0 || small <= 0)
+        return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    const uint8_t* dat = static_cast<const uint8_t*>(dat_v);
+    uint8_t* dst = static_cast<uint8_t*>(shard_out);
+    const int k = e->k;
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    cudaStream_t s = pick_stream(e, stream);
+    const int64_t large_row = large * k, small_row = small * k;
+    const int64_t nlarge = dat_size / large_row;
+    if (nlarge)
+        SWEC_CUDA(cudaMemcpy2DAsync(dst, size_t(large), dat + int64_t(shard_id) * large, size_t(large_row), size_t(large),
+                                    size_t(nlarge), cudaMemcpyDeviceToDevice, s));
+    const int64_t rem = dat_size - nlarge * large_row;
+    if (rem > 0) {
+        const uint8_t* base = dat + nlarge * large_row;
+        uint8_t* d2 = dst + nlarge * large;
+        const int64_t nfull = rem / small_row;
+        if (nfull)
+            SWEC_CUDA(cudaMemcpy2DAsync(d2, size_t(small), base + int64_t(shard_id) * small, size_t(small_row),
+                                        size_t(small), size_t(nfull), cudaMemcpyDeviceToDevice, s));
+        const int64_t tail = rem - nfull * small_row;
+        if (tail > 0) {
+            uint8_t* d3 = d2 + nfull * small;
+            int64_t have = tail - int64_t(shard_id) * small;
+            have = std::max<int64_t>(0, std::min(have, small));
+            if (have) SWEC_CUDA(cudaMemcpyAsync(d3, base + nfull * small_row + int64_t(shard_id) * small, size_t(have), cudaMemcpyDeviceToDevice, s));
+            if (have < small) SWEC_CUDA(cudaMemsetAsync(d3 + have, 0, size_t(small - have), s));
+        }
+    }
+    return SWEC_OK;
+}
+
+int swec_stream_synchronize(swec_encoder* e, void* stream) {
+    if (!e) return fail(SWEC_ERR_INVALID_ARG, "NULL encoder");
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    SWEC_CUDA(cudaStreamSynchronize(pick_stream(e, stream)));
+    return SWEC_OK;
+}
+
+// ---- pinned memory, measurement helpers
+
+void* swec_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void swec_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int swec_synth_fill_device(int device, void* dst, uint64_t byte_offset, size_t bytes, uint64_t seed, void* stream) {
+    if (!dst || (byte_offset & 7) || (bytes & 7) || (reinterpret_cast<uintptr_t>(dst) & 7))
+        return fail(SWEC_ERR_INVALID_ARG, "synth fill needs 8-byte aligned offset, size and pointer");
+    SWEC_CUDA(cudaSetDevice(device));
+    SWEC_CUDA(launch_synth(dst, byte_offset, bytes, seed, static_cast<cudaStream_t>(stream)));
+    return SWEC_OK;
+}
+
+int swec_digest_device(int device, const void* src, size_t bytes, uint64_t* digest, void* stream) {
+    if (!src || !digest) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    SWEC_CUDA(cudaSetDevice(device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    u64* d = nullptr;
+    SWEC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d), 8, s));
+    cudaError_t e = launch_digest(src, bytes, d, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(digest, d, 8, cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d, s);
+    if (e != cudaSuccess) return cuda_fail(e, "digest");
+    SWEC_CUDA(cudaStreamSynchronize(s));
+    return SWEC_OK;
+}
+
+}  // extern "C"

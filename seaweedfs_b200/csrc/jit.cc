@@ -1,0 +1,160 @@
+// seaweedfs_b200/csrc/jit.cc — run-time specialisation of the Horner kernel for a given matrix.
+//
+// Reconstruct matrices depend on which shards survived (1001 ten-of-fourteen subsets for
+// RS(10,4)), so they cannot all be compiled ahead of time.  The same generator that produced the
+// AOT encode kernel (codegen.cc) emits the straight-line combine() for the fused decode matrix;
+// NVRTC compiles it for sm_100a (≈0.3 s, once per matrix per process) and the cubin is loaded
+// through the runtime's library API.  This is the GPU analogue of klauspost's cached inversion
+// tree / the Rust twin's LRU of decode matrices (core.rs:25,700-734): the cache holds kernels.
+//
+// NVRTC is dlopen'ed so that libswec.so itself has no load-time dependency beyond cudart; if it
+// cannot be found the engine uses the shared-memory table kernel instead (still on the GPU).
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "codegen.h"
+#include "engine.h"
+
+namespace swec {
+
+static const char kDeviceCommonSrc[] =
+#include "device_common_src.inc"
+    ;
+
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t flat = nullptr, blocked = nullptr;
+    CodegenStats stats;
+};
+
+namespace {
+
+struct Nvrtc {
+    void* handle = nullptr;
+    decltype(&nvrtcCreateProgram) create = nullptr;
+    decltype(&nvrtcCompileProgram) compile = nullptr;
+    decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+    decltype(&nvrtcGetCUBIN) cubin = nullptr;
+    decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+    decltype(&nvrtcGetProgramLog) log = nullptr;
+    decltype(&nvrtcDestroyProgram) destroy = nullptr;
+    bool ok = false;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n = [] {
+        Nvrtc r;
+        if (getenv("SWEC_NO_JIT")) return r;
+        const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char* nm : names) {
+            r.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (r.handle) break;
+        }
+        if (!r.handle) return r;
+#define SWEC_SYM(field, name) r.field = reinterpret_cast<decltype(r.field)>(dlsym(r.handle, name))
+        SWEC_SYM(create, "nvrtcCreateProgram");
+        SWEC_SYM(compile, "nvrtcCompileProgram");
+        SWEC_SYM(cubin_size, "nvrtcGetCUBINSize");
+        SWEC_SYM(cubin, "nvrtcGetCUBIN");
+        SWEC_SYM(log_size, "nvrtcGetProgramLogSize");
+        SWEC_SYM(log, "nvrtcGetProgramLog");
+        SWEC_SYM(destroy, "nvrtcDestroyProgram");
+#undef SWEC_SYM
+        r.ok = r.create && r.compile && r.cubin_size && r.cubin && r.log_size && r.log && r.destroy;
+        return r;
+    }();
+    return n;
+}
+
+std::mutex g_jit_mu;
+std::map<std::vector<uint8_t>, std::shared_ptr<JitKernel>> g_jit_cache;  // process-wide
+
+}  // namespace
+
+bool jit_available() { return nvrtc().ok; }
+
+int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out) {
+    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols)};
+    key.insert(key.end(), rows.v.begin(), rows.v.end());
+    auto local = enc->jit.find(key);
+    if (local != enc->jit.end()) {
+        *out = local->second;
+        return SWEC_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_jit_mu);
+    auto it = g_jit_cache.find(key);
+    if (it != g_jit_cache.end()) {
+        enc->jit[key] = it->second;
+        *out = it->second;
+        return it->second ? SWEC_OK : SWEC_ERR_JIT;
+    }
+    Nvrtc& n = nvrtc();
+    if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
+    if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
+
+    auto kernel = std::make_shared<JitKernel>();
+    std::string src = "#define SWEC_XT_VARIANT 0\n";
+    src += kDeviceCommonSrc;
+    src += generate_combine(rows, "SwecJit", CodegenOptions{}, &kernel->stats);
+    src +=
+        "extern \"C\" __global__ void __launch_bounds__(256) swec_jit_flat(const __grid_constant__ SwecApplyParams p) {\n"
+        "    swec_horner_body<SwecJit, false>(p);\n}\n"
+        "extern \"C\" __global__ void __launch_bounds__(256) swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
+        "    swec_horner_body<SwecJit, true>(p);\n}\n";
+
+    nvrtcProgram prog = nullptr;
+    if (n.create(&prog, src.c_str(), "swec_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+        g_jit_cache[key] = nullptr;
+        return fail(SWEC_ERR_JIT, "nvrtcCreateProgram failed");
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    const nvrtcResult cr = n.compile(prog, 3, opts);
+    if (cr != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        n.log_size(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) n.log(prog, &log[0]);
+        n.destroy(&prog);
+        g_jit_cache[key] = nullptr;
+        return fail(SWEC_ERR_JIT, "NVRTC compile failed: " + log);
+    }
+    size_t cs = 0;
+    n.cubin_size(prog, &cs);
+    std::vector<char> cubin(cs);
+    n.cubin(prog, cubin.data());
+    n.destroy(&prog);
+
+    cudaError_t e = cudaLibraryLoadData(&kernel->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->flat, kernel->lib, "swec_jit_flat");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->blocked, kernel->lib, "swec_jit_blocked");
+    if (e != cudaSuccess) {
+        g_jit_cache[key] = nullptr;
+        cuda_fail(e, "loading the specialised kernel");
+        return SWEC_ERR_JIT;
+    }
+    g_jit_cache[key] = kernel;
+    enc->jit[key] = kernel;
+    *out = kernel;
+    return SWEC_OK;
+}
+
+cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocked, cudaStream_t s) {
+    if (p.nvec == 0) return cudaSuccess;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const u64 need = (p.nvec + 255) / 256;
+    const u64 cap = u64(sms) * u64(encode_ctas_per_sm());
+    const unsigned grid = unsigned(need < cap ? need : cap);
+    void* args[] = {const_cast<SwecApplyParams*>(&p)};
+    g_kernel_launches++;
+    return cudaLaunchKernel(reinterpret_cast<const void*>(blocked ? k.blocked : k.flat), dim3(grid), dim3(256), args, 0, s);
+}
+
+}  // namespace swec

@@ -1,0 +1,26 @@
+// seaweedfs_b200/csrc/kernels.h — host-callable launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "apply_params.h"
+
+namespace swec {
+
+extern std::atomic<unsigned long long> g_kernel_launches;
+
+// tuning knob (resident CTAs per SM the persistent grids are sized for); SWEC_CTAS_PER_SM overrides
+int encode_ctas_per_sm();
+
+cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStream_t s);
+// replicated_tables: [K][2][16][32] words (lane-replicated), device memory, 16-byte aligned
+cudaError_t launch_table_apply(const SwecApplyParams& p, const u32* replicated_tables, int K, int r, cudaStream_t s);
+// compact_tables: [K][2][16] words, device memory
+cudaError_t launch_bytes_apply(const SwecApplyParams& p, const u32* compact_tables, int K, int r, u64 nbytes,
+                               cudaStream_t s);
+cudaError_t launch_synth(void* dst, u64 byte_offset, u64 nbytes, u64 seed, cudaStream_t s);
+cudaError_t launch_digest(const void* src, u64 nbytes, u64* out_dev, cudaStream_t s);
+cudaError_t launch_compare(const void* a, const void* b, u64 nbytes, unsigned long long* out_dev, cudaStream_t s);
+
+}  // namespace swec

@@ -1,0 +1,247 @@
+"""Host-side mirror of SeaweedFS's ``weed/storage/erasure_coding`` package surface for the RS hot
+path, bound to libswec.so.  Names follow the Go package (Go spelling kept as aliases) so the parity
+tests read like the reference's own tests:
+
+    ECContext / NewDefaultECContext / CreateEncoder       ec_context.go:11-46
+    Encoder.Encode / Reconstruct / ReconstructData        klauspost Encoder, call sites
+                                                          ec_encoder.go:265,360; store_ec.go:551
+    WriteEcFiles / generateEcFiles / RebuildEcFiles       ec_encoder.go:61-128,146-200
+    WriteDatFile                                          ec_decoder.go:176-223
+    LocateData / Interval.ToShardIdAndOffset              ec_locate.go:16-98
+
+Buffers are numpy uint8 arrays (host) or raw device pointers (ints) for the ``*_device`` calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._native import Interval, SwecError, check, lib
+
+DataShardsCount = 10                               # ec_encoder.go:20
+ParityShardsCount = 4                              # ec_encoder.go:21
+TotalShardsCount = DataShardsCount + ParityShardsCount
+MaxShardCount = 32                                 # ec_encoder.go:23
+ErasureCodingLargeBlockSize = 1024 * 1024 * 1024   # ec_encoder.go:25
+ErasureCodingSmallBlockSize = 1024 * 1024          # ec_encoder.go:26
+
+
+def _ptrs(arrs) -> C.Array:
+    out = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        if a is None:
+            out[i] = None
+        elif isinstance(a, np.ndarray):
+            out[i] = a.ctypes.data
+        else:
+            out[i] = int(a)
+    return out
+
+
+class Encoder:
+    """reedsolomon.Encoder backed by the B200 engine (swec_encoder)."""
+
+    def __init__(self, data_shards: int, parity_shards: int, device: int = 0):
+        h = C.c_void_p()
+        check(lib().swec_encoder_new(data_shards, parity_shards, device, C.byref(h)))
+        self._h = h
+        self.data_shards, self.parity_shards, self.device = data_shards, parity_shards, device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().swec_encoder_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def total_shards(self) -> int:
+        return self.data_shards + self.parity_shards
+
+    def matrix(self) -> np.ndarray:
+        m = np.zeros((self.total_shards, self.data_shards), dtype=np.uint8)
+        check(lib().swec_encoder_matrix(self._h, m.ctypes.data))
+        return m
+
+    def reconstruct_matrix(self, present, data_only: bool = False):
+        pres = np.ascontiguousarray(np.asarray(present, dtype=np.uint8))
+        inputs = (C.c_int * self.data_shards)()
+        outputs = (C.c_int * self.total_shards)()
+        n = C.c_int(0)
+        rows = np.zeros((self.total_shards, self.data_shards), dtype=np.uint8)
+        check(lib().swec_reconstruct_matrix(self._h, pres.ctypes.data, int(data_only), inputs, outputs,
+                                            C.byref(n), rows.ctypes.data))
+        return list(inputs), list(outputs[: n.value]), rows[: n.value].copy()
+
+    # -- host buffers ---------------------------------------------------------------------------
+    def _check_shards(self, shards, allow_missing: bool):
+        if len(shards) != self.total_shards:
+            raise SwecError(-1, f"need {self.total_shards} shards, got {len(shards)} (ErrTooFewShards)")
+        n = None
+        for s in shards:
+            if s is None or (allow_missing and len(s) == 0):
+                if not allow_missing:
+                    raise SwecError(-1, "nil shard")
+                continue
+            if s.dtype != np.uint8 or not s.flags["C_CONTIGUOUS"]:
+                raise SwecError(-1, "shards must be contiguous uint8 arrays")
+            if n is None:
+                n = s.shape[0]
+            elif s.shape[0] != n:
+                raise SwecError(-6, "shards are of different sizes (ErrShardSize)")
+        if not n:
+            raise SwecError(-1, "no shard data (ErrShardNoData)")
+        return n
+
+    def encode(self, shards: list[np.ndarray]) -> None:
+        """Encode(shards [][]byte): parity slices (last m) are overwritten in place."""
+        n = self._check_shards(shards, allow_missing=False)
+        check(lib().swec_encode(self._h, _ptrs(shards), n))
+
+    def reconstruct(self, shards: list, data_only: bool = False) -> None:
+        """Reconstruct(shards): None / empty entries are missing and are replaced by new arrays."""
+        n = self._check_shards(shards, allow_missing=True)
+        present = np.array([s is not None and len(s) > 0 for s in shards], dtype=np.uint8)
+        if present.sum() < self.data_shards:
+            raise SwecError(-2, "too few shards given (ErrTooFewShards)")
+        for i in range(self.total_shards):
+            if not present[i] and (i < self.data_shards or not data_only):
+                shards[i] = np.zeros(n, dtype=np.uint8)
+        bufs = [s if s is not None and len(s) else None for s in shards]
+        check(lib().swec_reconstruct(self._h, _ptrs(bufs), present.ctypes.data, n, int(data_only)))
+
+    def reconstruct_data(self, shards: list) -> None:
+        self.reconstruct(shards, data_only=True)
+
+    def verify(self, shards: list[np.ndarray]) -> bool:
+        n = self._check_shards(shards, allow_missing=False)
+        ok = C.c_int(0)
+        check(lib().swec_verify(self._h, _ptrs(shards), n, C.byref(ok)))
+        return bool(ok.value)
+
+    # -- device buffers (raw pointers), asynchronous on `stream` ----------------------------------
+    def encode_device(self, data_ptrs, parity_ptrs, shard_len: int, stream: int = 0) -> None:
+        check(lib().swec_encode_device(self._h, _ptrs(data_ptrs), _ptrs(parity_ptrs), shard_len, stream))
+
+    def reconstruct_device(self, shard_ptrs, present, shard_len: int, data_only: bool = False, stream: int = 0) -> None:
+        pres = np.ascontiguousarray(np.asarray(present, dtype=np.uint8))
+        check(lib().swec_reconstruct_device(self._h, _ptrs(shard_ptrs), pres.ctypes.data, shard_len,
+                                            int(data_only), stream))
+
+    def encode_volume_device(self, dat_ptr: int, dat_size: int, parity_ptrs, stream: int = 0,
+                             large_block: int = ErasureCodingLargeBlockSize,
+                             small_block: int = ErasureCodingSmallBlockSize) -> None:
+        check(lib().swec_encode_volume_device(self._h, dat_ptr, dat_size, large_block, small_block,
+                                              _ptrs(parity_ptrs), stream))
+
+    def extract_data_shard_device(self, dat_ptr: int, dat_size: int, shard_id: int, out_ptr: int, stream: int = 0,
+                                  large_block: int = ErasureCodingLargeBlockSize,
+                                  small_block: int = ErasureCodingSmallBlockSize) -> None:
+        check(lib().swec_extract_data_shard_device(self._h, dat_ptr, dat_size, large_block, small_block,
+                                                   shard_id, out_ptr, stream))
+
+    def synchronize(self, stream: int = 0) -> None:
+        check(lib().swec_stream_synchronize(self._h, stream))
+
+    # Go spellings
+    Encode, Reconstruct, ReconstructData, Verify = encode, reconstruct, reconstruct_data, verify
+
+
+@dataclass
+class ECContext:
+    """ec_context.go:11-46"""
+    DataShards: int = DataShardsCount
+    ParityShards: int = ParityShardsCount
+    Collection: str = ""
+    VolumeId: int = 0
+    device: int = 0
+
+    def Total(self) -> int:
+        return self.DataShards + self.ParityShards
+
+    def CreateEncoder(self) -> Encoder:
+        return Encoder(self.DataShards, self.ParityShards, self.device)
+
+    def ToExt(self, shard_index: int) -> str:
+        return ".ec%02d" % shard_index
+
+    def String(self) -> str:
+        return "%d+%d (total: %d)" % (self.DataShards, self.ParityShards, self.Total())
+
+
+def NewDefaultECContext(collection: str = "", volume_id: int = 0, device: int = 0) -> ECContext:
+    return ECContext(DataShardsCount, ParityShardsCount, collection, volume_id, device)
+
+
+def ToExt(ec_index: int) -> str:
+    return ".ec%02d" % ec_index
+
+
+# ---- file level ---------------------------------------------------------------------------------
+
+def generate_ec_files(base_file_name: str, buffer_size: int, large_block_size: int, small_block_size: int,
+                      ctx: ECContext | None = None) -> None:
+    ctx = ctx or NewDefaultECContext()
+    check(lib().swec_generate_ec_files(base_file_name.encode(), buffer_size, large_block_size, small_block_size,
+                                       ctx.DataShards, ctx.ParityShards, ctx.device))
+
+
+def write_ec_files(base_file_name: str, ctx: ECContext | None = None) -> None:
+    generate_ec_files(base_file_name, 256 * 1024, ErasureCodingLargeBlockSize, ErasureCodingSmallBlockSize, ctx)
+
+
+def rebuild_ec_files(base_file_name: str, additional_dirs: list[str] | None = None,
+                     ctx: ECContext | None = None, device: int = 0) -> list[int]:
+    """RebuildEcFiles (ctx None ⇒ ratio from .vif or 10+4) / RebuildEcFilesWithContext."""
+    dirs = [d.encode() for d in (additional_dirs or [])]
+    arr = (C.c_char_p * max(1, len(dirs)))(*dirs) if dirs else None
+    ids = (C.c_uint32 * MaxShardCount)()
+    n = C.c_int(0)
+    k, m, dev = (ctx.DataShards, ctx.ParityShards, ctx.device) if ctx else (0, 0, device)
+    check(lib().swec_rebuild_ec_files(base_file_name.encode(), arr, len(dirs), k, m, dev, ids, C.byref(n)))
+    return list(ids[: n.value])
+
+
+def write_dat_file(base_file_name: str, dat_file_size: int, shard_file_names: list[str],
+                   data_shards: int = DataShardsCount, large_block: int = ErasureCodingLargeBlockSize,
+                   small_block: int = ErasureCodingSmallBlockSize) -> None:
+    names = (C.c_char_p * len(shard_file_names))(*[s.encode() for s in shard_file_names])
+    check(lib().swec_write_dat_file(base_file_name.encode(), dat_file_size, names, data_shards, large_block, small_block))
+
+
+WriteEcFiles, WriteEcFilesWithContext = write_ec_files, write_ec_files
+generateEcFiles, RebuildEcFiles, WriteDatFile = generate_ec_files, rebuild_ec_files, write_dat_file
+
+
+# ---- layout --------------------------------------------------------------------------------------
+
+def expected_shard_size(dat_size: int, data_shards: int = DataShardsCount,
+                        large_block: int = ErasureCodingLargeBlockSize,
+                        small_block: int = ErasureCodingSmallBlockSize) -> int:
+    return int(lib().swec_expected_shard_size(dat_size, data_shards, large_block, small_block))
+
+
+def locate_data(large_block_length: int, small_block_length: int, shard_dat_size: int, offset: int, size: int,
+                data_shards: int = DataShardsCount):
+    """LocateData → list of (BlockIndex, InnerBlockOffset, Size, IsLargeBlock, LargeBlockRowsCount)."""
+    cap = 4 + int(size // max(1, small_block_length)) + 2
+    buf = (Interval * cap)()
+    n = lib().swec_locate_data(large_block_length, small_block_length, shard_dat_size, offset, size,
+                               data_shards, buf, cap)
+    if n < 0:
+        check(n)
+    return [(b.block_index, b.inner_block_offset, b.size, bool(b.is_large_block), b.large_block_rows_count)
+            for b in buf[:n]]
+
+
+def interval_to_shard(iv, large_block: int, small_block: int, data_shards: int = DataShardsCount):
+    """Interval.ToShardIdAndOffset"""
+    c = Interval(iv[0], int(iv[3]), iv[1], iv[2], iv[4], 0)
+    sid, off = C.c_int(0), C.c_int64(0)
+    lib().swec_interval_to_shard(C.byref(c), large_block, small_block, data_shards, C.byref(sid), C.byref(off))
+    return sid.value, off.value
+
+
+LocateData = locate_data

@@ -1,0 +1,171 @@
+"""CPU-only checks of the product's host side: libswec.so loads without a GPU, exports exactly
+what include/swec.h declares, its matrices and layout arithmetic agree with the oracle, and compute
+entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "swec.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(swec_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_library_agree(swec):
+    from seaweedfs_b200._native import PROTOTYPES, library_path
+    names = declared_functions()
+    assert len(names) >= 25
+    exported = subprocess.run(["nm", "-D", "--defined-only", library_path()], check=True,
+                              stdout=subprocess.PIPE, text=True).stdout
+    exported = set(re.findall(r" T (swec_[a-z0-9_]+)", exported))
+    assert set(names) == exported, (set(names) ^ exported)
+    assert set(names) == set(PROTOTYPES)
+    L = swec.lib()
+    for n in names:
+        assert getattr(L, n)
+
+
+def test_library_needs_no_gpu_to_load(swec):
+    out = subprocess.run(["ldd", swec.library_path()], check=True, stdout=subprocess.PIPE, text=True).stdout
+    assert "libcuda.so" not in out and "libnvrtc" not in out and "not found" not in out
+
+
+def test_library_is_sm100a_only(swec):
+    out = subprocess.run(["cuobjdump", "--list-elf", swec.library_path()], stdout=subprocess.PIPE, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_strerror_and_version(swec):
+    L = swec.lib()
+    assert b"sm_100a" in L.swec_version()
+    assert L.swec_strerror(0) == b"ok"
+    assert b"CPU fallback" in L.swec_strerror(-7)
+
+
+@pytest.mark.parametrize("k,m", [(10, 4), (5, 5), (3, 2), (12, 4), (20, 12), (1, 1), (16, 16)])
+def test_generator_matches_oracle(swec, oracle, k, m):
+    enc = swec.erasure_coding.Encoder(k, m, device=-1)
+    assert (enc.matrix() == oracle.build_matrix(k, k + m)).all()
+
+
+@pytest.mark.parametrize("bad", [(0, 4), (10, 0), (-1, 2), (30, 3), (32, 1)])
+def test_encoder_rejects_bad_ratios(swec, bad):
+    # reedsolomon.New → ErrInvShardNum ; SeaweedFS: ds+ps <= MaxShardCount (ec_encoder.go:81)
+    with pytest.raises(swec.SwecError) as e:
+        swec.erasure_coding.Encoder(bad[0], bad[1], device=-1)
+    assert e.value.name == "SWEC_ERR_INVALID_ARG"
+
+
+def test_reconstruct_matrix_matches_oracle(swec, kat):
+    from oracle import rs_numpy as rn
+    enc = swec.erasure_coding.Encoder(10, 4, device=-1)
+    rng = np.random.default_rng(11)
+    patterns = [[0, 1, 2, 3], [10, 11, 12, 13], [0, 1, 10, 11], [5], [13], [2, 7, 12]]
+    patterns += [sorted(rng.choice(14, size=rng.integers(1, 5), replace=False).tolist()) for _ in range(40)]
+    for erased in patterns:
+        present = [i not in erased for i in range(14)]
+        for data_only in (False, True):
+            valid, missing, rows = rn.fused_reconstruct_rows(10, 4, present, data_only)
+            ins, outs, got = enc.reconstruct_matrix(present, data_only)
+            assert ins == valid and outs == missing and (got == rows).all()
+    # SURVEY §8(c) worst case
+    _, _, rows = enc.reconstruct_matrix([0, 0, 0, 0] + [1] * 10)
+    assert rows[0].tolist() == [29, 239, 227, 16, 49, 195, 195, 48, 13, 12]
+    with pytest.raises(swec.SwecError) as e:
+        enc.reconstruct_matrix([0] * 5 + [1] * 9)
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS"
+
+
+def test_layout_matches_oracle(swec, oracle, kat):
+    ec = swec.erasure_coding
+    for case in kat["K7"]:
+        assert ec.LocateData(*case["args"]) == [tuple(iv) for iv in case["intervals"]]
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        large = int(rng.choice([10000, 1 << 20, 1 << 30]))
+        small = int(rng.choice([100, 4096, 1 << 20]))
+        if small > large:
+            continue
+        dat = int(rng.integers(1, 40 * large))
+        shard = ec.expected_shard_size(dat, 10, large, small)
+        assert shard == oracle.expected_shard_size(dat, 10, large, small)
+        off = int(rng.integers(0, dat))
+        size = int(rng.integers(1, min(dat - off, 5 * small) + 1))
+        want = oracle.locate_data(large, small, dat // 10, off, size)
+        got = ec.locate_data(large, small, dat // 10, off, size)
+        assert got == want
+        for iv in got:
+            from oracle import rs_numpy as rn
+            assert ec.interval_to_shard(iv, large, small) == rn.interval_to_shard(iv, large, small)
+
+
+def test_compute_fails_loudly_without_device(swec):
+    ec = swec.erasure_coding
+    enc = ec.Encoder(10, 4, device=-1)
+    shards = [np.zeros(64, dtype=np.uint8) for _ in range(14)]
+    with pytest.raises(swec.SwecError) as e:
+        enc.encode(shards)
+    assert e.value.name == "SWEC_ERR_NO_DEVICE"
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(swec.SwecError) as e2:
+            ec.Encoder(10, 4, device=0).encode(shards)
+        assert e2.value.name in ("SWEC_ERR_NO_DEVICE", "SWEC_ERR_CUDA")
+        n = C.c_int(-1)
+        assert swec.lib().swec_device_count(C.byref(n)) == -7 and n.value == 0
+
+
+def test_argument_validation(swec, tmp_path):
+    ec = swec.erasure_coding
+    enc = ec.Encoder(10, 4, device=-1)
+    with pytest.raises(swec.SwecError):
+        enc.encode([np.zeros(8, dtype=np.uint8)] * 13)            # wrong shard count
+    with pytest.raises(swec.SwecError):
+        enc.encode([np.zeros(8, dtype=np.uint8)] * 13 + [np.zeros(9, dtype=np.uint8)])  # ErrShardSize
+    with pytest.raises(swec.SwecError):
+        enc.reconstruct([None] * 5 + [np.zeros(8, dtype=np.uint8)] * 9)   # ErrTooFewShards
+    with pytest.raises(swec.SwecError) as e:
+        ec.generate_ec_files(str(tmp_path / "x"), 0, 1 << 30, 1 << 20)    # zero buffer (Fatal in Go)
+    assert e.value.name == "SWEC_ERR_INVALID_ARG"
+    with pytest.raises(swec.SwecError):
+        ec.generate_ec_files(str(tmp_path / "x"), 48, 10000, 100)         # block % buffer != 0
+    with pytest.raises(swec.SwecError) as e:
+        ec.generate_ec_files(str(tmp_path / "missing"), 50, 10000, 100)   # no .dat
+    assert e.value.name == "SWEC_ERR_IO"
+
+
+def test_rebuild_prechecks_need_no_gpu(swec, tmp_path):
+    """generateMissingEcFiles bails out before creating outputs when < k shards exist (ec_encoder.go:172-175)."""
+    ec = swec.erasure_coding
+    base = str(tmp_path / "3")
+    for i in range(9):
+        open(base + ec.ToExt(i), "wb").write(b"\0" * 16)
+    with pytest.raises(swec.SwecError) as e:
+        ec.rebuild_ec_files(base)
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS"
+    assert sorted(os.listdir(tmp_path)) == ["3.ec%02d" % i for i in range(9)]
+    # all shards present: nothing to do, no device touched
+    for i in range(9, 14):
+        open(base + ec.ToExt(i), "wb").write(b"\0" * 16)
+    assert ec.rebuild_ec_files(base) == []
+
+
+def test_write_dat_file_roundtrip(swec, oracle, tmp_path):
+    ec = swec.erasure_coding
+    rng = np.random.default_rng(9)
+    dat = rng.integers(0, 256, 1_234_567, dtype=np.uint8)
+    shards = oracle.encode_dat_image(dat, buffer_size=50, large=10000, small=100)
+    names = []
+    for i in range(10):
+        names.append(str(tmp_path / ("5.ec%02d" % i)))
+        shards[i].tofile(names[-1])
+    ec.write_dat_file(str(tmp_path / "out"), len(dat), names, 10, 10000, 100)
+    assert (np.fromfile(str(tmp_path / "out.dat"), dtype=np.uint8) == dat).all()

@@ -1,0 +1,496 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs (bit-exact), the committed golden digests, and — at BASELINE.json's full sizes —
+size-independent properties (device digests of encode→erase→reconstruct round trips, linearity)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DAT = os.path.join(ROOT, "oracle", "_ref", "1.dat")
+SEED = 0x5EA3EED5F00DCAFE
+
+
+def dev(torch, arr):
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+def stream(torch):
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.fixture(scope="module")
+def enc(swec, cuda):
+    e = swec.erasure_coding.Encoder(10, 4, device=0)
+    yield e
+    e.close()
+
+
+# ---------------------------------------------------------------- Encode (ec_encoder.go:265)
+
+@pytest.mark.parametrize("n", [16, 4096, 4096 + 16, 1 << 20, (1 << 20) + 48, 3_000_000 - 3_000_000 % 16])
+def test_encode_device_matches_oracle(cuda, enc, oracle, n):
+    torch = cuda
+    rng = np.random.default_rng(n)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    want = oracle.encode(10, 4, data)
+    d = [dev(torch, x) for x in data]
+    p = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    enc.encode_device([t.data_ptr() for t in d], [t.data_ptr() for t in p], n, stream(torch))
+    torch.cuda.synchronize()
+    for got, w in zip(p, want):
+        assert (got.cpu().numpy() == w).all()
+
+
+@pytest.mark.parametrize("n,shift", [(1, 0), (7, 0), (15, 3), (17, 0), (1000, 1), (65536 + 5, 0), (4099, 5)])
+def test_encode_device_ragged_and_unaligned(cuda, enc, oracle, n, shift):
+    """<16-byte tails and pointers that are not 16-byte aligned take the byte-granular kernel."""
+    torch = cuda
+    rng = np.random.default_rng(n * 31 + shift)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    want = oracle.encode(10, 4, data)
+    backing = [torch.zeros(n + 64, dtype=torch.uint8, device="cuda") for _ in range(14)]
+    views = [b[shift:shift + n] for b in backing]
+    for v, x in zip(views[:10], data):
+        v.copy_(torch.from_numpy(x))
+    enc.encode_device([v.data_ptr() for v in views[:10]], [v.data_ptr() for v in views[10:]], n, stream(torch))
+    torch.cuda.synchronize()
+    for v, w, b in zip(views[10:], want, backing[10:]):
+        assert (v.cpu().numpy() == w).all()
+        assert int(b[:shift].sum()) == 0 and int(b[shift + n:].sum()) == 0   # no stray writes
+
+
+@pytest.mark.parametrize("pattern", ["zeros", "ones", "i_plus_j", "seven_i", "single_bits"])
+def test_encode_adversarial_patterns(cuda, enc, oracle, kat, pattern):
+    torch = cuda
+    n = 4096
+    if pattern == "zeros":
+        data = [np.zeros(n, dtype=np.uint8) for _ in range(10)]
+    elif pattern == "ones":
+        data = [np.full(n, 255, dtype=np.uint8) for _ in range(10)]
+    elif pattern == "i_plus_j":     # weed/storage/store_ec_recovery_test.go:208-213
+        data = [((np.arange(n) + i) & 255).astype(np.uint8) for i in range(10)]
+    elif pattern == "seven_i":      # seaweed-volume/src/storage/erasure_coding/ec_encoder.rs:666-674
+        data = [np.full(n, (7 * i) & 255, dtype=np.uint8) for i in range(10)]
+    else:
+        data = [np.zeros(n, dtype=np.uint8) for _ in range(10)]
+        for j in range(n):
+            data[j % 10][j] = 1 << ((j // 10) % 8)
+    shards = data + [np.zeros(n, dtype=np.uint8) for _ in range(4)]
+    enc.encode(shards)                                      # host path (Encoder.Encode)
+    want = oracle.encode(10, 4, data)
+    for got, w in zip(shards[10:], want):
+        assert (got == w).all()
+    if pattern == "seven_i":
+        assert [int(s[0]) for s in shards[10:]] == kat["K9"]["seven_i"]
+    if pattern == "i_plus_j":
+        assert [[int(s[j]) for s in shards[10:]] for j in range(4)] == kat["K9"]["i_plus_j"]
+
+
+@pytest.mark.parametrize("n", [1, 50, 256 * 1024, 5 * 1024 * 1024 + 77])
+def test_encode_host_pageable_and_pinned(cuda, swec, enc, oracle, n):
+    """Encoder.Encode on host memory: 256 KiB is the reference's production batch (ec_encoder.go:68);
+    the largest size spans several staging chunks; pinned buffers take the direct-DMA branch."""
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    want = oracle.encode(10, 4, data)
+    shards = [x.copy() for x in data] + [np.full(n, 0xAA, dtype=np.uint8) for _ in range(4)]
+    enc.encode(shards)
+    for i in range(10):
+        assert (shards[i] == data[i]).all()               # data untouched
+    for got, w in zip(shards[10:], want):
+        assert (got == w).all()
+    L = swec.lib()
+    raw = L.swec_alloc_pinned(14 * n)
+    assert raw
+    try:
+        buf = np.ctypeslib.as_array(C.cast(raw, C.POINTER(C.c_uint8)), shape=(14 * n,))
+        pinned = [buf[i * n:(i + 1) * n] for i in range(14)]
+        for v, x in zip(pinned[:10], data):
+            v[:] = x
+        enc.encode(pinned)
+        for got, w in zip(pinned[10:], want):
+            assert (got == w).all()
+    finally:
+        L.swec_free_pinned(raw)
+
+
+# ---------------------------------------------------------------- Reconstruct (ec_encoder.go:360, store_ec.go:551)
+
+def all_patterns(limit, seed=1):
+    import itertools
+    pats = [p for r in range(1, 5) for p in itertools.combinations(range(14), r)]
+    rng = np.random.default_rng(seed)
+    pick = rng.choice(len(pats), size=limit, replace=False)
+    must = [(0, 1, 2, 3), (10, 11, 12, 13), (0, 1, 10, 11), (5,), (13,), (6, 7, 8, 9)]
+    return must + [pats[i] for i in pick]
+
+
+def test_reconstruct_host_many_patterns(cuda, enc, oracle):
+    n = 70_001
+    rng = np.random.default_rng(42)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    full = data + oracle.encode(10, 4, data)
+    for erased in all_patterns(60):
+        shards = [None if i in erased else s.copy() for i, s in enumerate(full)]
+        enc.reconstruct(shards)
+        for i in range(14):
+            assert (shards[i] == full[i]).all(), (erased, i)
+        shards = [None if i in erased else s.copy() for i, s in enumerate(full)]
+        enc.reconstruct_data(shards)                        # ReconstructData: parity stays missing
+        for i in range(14):
+            if i < 10:
+                assert (shards[i] == full[i]).all(), (erased, i)
+            elif i in erased:
+                assert shards[i] is None
+
+
+def test_reconstruct_degraded_read_pattern(cuda, swec, oracle):
+    """store_ec_recovery_test.go:194-249: byte(i+j) pattern, drop shard 5, ReconstructData(bufs[:14])."""
+    enc = swec.erasure_coding.Encoder(10, 4, device=0)      # reedsolomon.New per call, store_ec.go:485
+    n = 1024
+    data = [((np.arange(n) + i) & 255).astype(np.uint8) for i in range(10)]
+    full = data + oracle.encode(10, 4, data)
+    bufs = [s.copy() for s in full]
+    bufs[5] = None
+    enc.reconstruct_data(bufs)
+    assert (bufs[5] == full[5]).all()
+    for p in range(10, 14):                                  # :252-298 — drop each parity, Reconstruct
+        bufs = [s.copy() for s in full]
+        bufs[p] = None
+        enc.reconstruct(bufs)
+        assert (bufs[p] == full[p]).all()
+
+
+def test_reconstruct_device_jit_and_tables_agree(cuda, swec, oracle, monkeypatch):
+    """Both run-time-matrix kernels (NVRTC-specialised Horner, shared-memory tables) against the oracle."""
+    torch = cuda
+    n = 1 << 20
+    rng = np.random.default_rng(8)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    full = data + oracle.encode(10, 4, data)
+    for min_bytes in ("1", str(1 << 40)):                    # force JIT / force tables
+        monkeypatch.setenv("SWEC_JIT_MIN_BYTES", min_bytes)
+        for erased in [(0, 1, 2, 3), (2, 11), (10, 13), (4, 5, 6, 12)]:
+            enc = swec.erasure_coding.Encoder(10, 4, device=0)
+            t = [dev(torch, s) if i not in erased else torch.zeros(n, dtype=torch.uint8, device="cuda")
+                 for i, s in enumerate(full)]
+            enc.reconstruct_device([x.data_ptr() for x in t], [i not in erased for i in range(14)], n, False, stream(torch))
+            torch.cuda.synchronize()
+            for i in erased:
+                assert (t[i].cpu().numpy() == full[i]).all(), (min_bytes, erased, i)
+            enc.close()
+
+
+def test_reconstruct_errors(cuda, enc):
+    shards = [None] * 5 + [np.zeros(64, dtype=np.uint8) for _ in range(9)]
+    with pytest.raises(Exception) as e:
+        enc.reconstruct(shards)
+    assert "TOO_FEW" in str(e.value) or "too few" in str(e.value)
+    ok = [np.zeros(64, dtype=np.uint8) for _ in range(14)]
+    enc.reconstruct(ok)                                       # all present: no-op
+
+
+def test_verify(cuda, enc, oracle):
+    n = 300_000
+    rng = np.random.default_rng(5)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    full = data + oracle.encode(10, 4, data)
+    assert enc.verify(full) is True
+    full[12][n - 1] ^= 1                                      # core.rs test_one_encode: +1 breaks verify
+    assert enc.verify(full) is False
+    full[12][n - 1] ^= 1
+    full[3][0] ^= 0x80
+    assert enc.verify(full) is False
+
+
+@pytest.mark.parametrize("k,m", [(5, 5), (3, 2), (12, 4), (20, 12), (6, 3)])
+def test_custom_ratios(cuda, swec, oracle, kat, k, m):
+    """.vif EcShardConfig ratios (ds+ps <= 32, ec_encoder.go:77-91) keep working."""
+    enc = swec.erasure_coding.Encoder(k, m, device=0)
+    n = 100_003
+    rng = np.random.default_rng(k * 100 + m)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(k)]
+    want = oracle.encode(k, m, data)
+    shards = [x.copy() for x in data] + [np.zeros(n, dtype=np.uint8) for _ in range(m)]
+    enc.encode(shards)
+    for got, w in zip(shards[k:], want):
+        assert (got == w).all()
+    erased = list(rng.choice(k + m, size=min(m, 3), replace=False))
+    holes = [None if i in erased else s.copy() for i, s in enumerate(shards)]
+    enc.reconstruct(holes)
+    for i in range(k + m):
+        assert (holes[i] == shards[i]).all()
+    if (k, m) == (5, 5):                                      # K5, tests/mod.rs:851-893
+        d = [np.array(x, dtype=np.uint8) for x in kat["K5"]["data"]] + [np.zeros(2, dtype=np.uint8) for _ in range(5)]
+        enc.encode(d)
+        assert [x.tolist() for x in d[5:]] == kat["K5"]["parity"]
+    enc.close()
+
+
+# ---------------------------------------------------------------- volume image → shards (ec_encoder.go:280-321)
+
+def encode_volume_on_device(torch, enc, dat, large, small):
+    from seaweedfs_b200 import erasure_coding as ec
+    n = len(dat)
+    shard = ec.expected_shard_size(n, 10, large, small)
+    d = dev(torch, dat) if n else torch.zeros(16, dtype=torch.uint8, device="cuda")
+    par = [torch.full((max(shard, 1),), 0x55, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    enc.encode_volume_device(d.data_ptr(), n, [p.data_ptr() for p in par], stream(torch), large, small)
+    shards = []
+    for i in range(10):
+        o = torch.full((max(shard, 1),), 0x66, dtype=torch.uint8, device="cuda")
+        enc.extract_data_shard_device(d.data_ptr(), n, i, o.data_ptr(), stream(torch), large, small)
+        shards.append(o)
+    torch.cuda.synchronize()
+    return [s[:shard].cpu().numpy() for s in shards + par]
+
+
+@pytest.mark.parametrize("size,large,small", [
+    (1, 1 << 30, 1 << 20),
+    (10 * (1 << 20), 1 << 30, 1 << 20),
+    (10 * (1 << 20) + 1, 1 << 30, 1 << 20),
+    (33_333_333, 1 << 30, 1 << 20),
+    (2_590_912, 10000, 100),                  # ec_test.go:19-30 block sizes (unaligned blocks)
+    (10 * 4096 * 5 + 10 * 512 * 3 + 77, 4096, 512),   # large rows + small rows + ragged tail, aligned blocks
+    (10 * 4096 * 3, 4096, 512),               # exact multiple of the large row (Issue 8947 shape)
+    (10 * 4096 * 2 + 10 * 512 * 4, 4096, 512),
+])
+def test_encode_volume_device_layout(cuda, enc, oracle, size, large, small):
+    torch = cuda
+    dat = oracle.synth(0, size, SEED + size)
+    want = oracle.encode_dat_image(dat, buffer_size=np.gcd(large, small).item(), large=large, small=small)
+    got = encode_volume_on_device(torch, enc, dat, large, small)
+    for i in range(14):
+        assert got[i].shape == want[i].shape and (got[i] == want[i]).all(), i
+
+
+def test_fixture_1dat_digests(cuda, enc, kat):
+    """K8: the reference's own fixture volume, shards byte-identical to the reference arithmetic."""
+    if not os.path.exists(REF_DAT):
+        pytest.skip("oracle/_ref/1.dat not shipped")
+    dat = np.fromfile(REF_DAT, dtype=np.uint8)
+    for label in ("production", "test"):
+        g = kat["K8"][label]
+        got = encode_volume_on_device(cuda, enc, dat, g["large"], g["small"])
+        assert [hashlib.sha256(s.tobytes()).hexdigest() for s in got] == g["sha256"]
+
+
+# ---------------------------------------------------------------- files (ec_encoder.go:61-200)
+
+def test_generate_and_rebuild_ec_files(cuda, swec, oracle, tmp_path):
+    ec = swec.erasure_coding
+    size = 23_456_789
+    dat = oracle.synth(0, size, SEED)
+    base = str(tmp_path / "11")
+    dat.tofile(base + ".dat")
+    ec.write_ec_files(base)                                   # WriteEcFiles: 10+4, 1 GiB / 1 MiB
+    want = oracle.encode_dat_image(dat)
+    for i in range(14):
+        got = np.fromfile(base + ec.ToExt(i), dtype=np.uint8)
+        assert got.shape == want[i].shape and (got == want[i]).all(), i
+    assert os.path.getsize(base + ".ec00") == ec.expected_shard_size(size)
+    # ec.rebuild: drop 4 shards (worst case), one survivor lives on another disk (additionalDirs)
+    other = tmp_path / "disk2"
+    other.mkdir()
+    os.rename(base + ".ec05", str(other / "11.ec05"))
+    for i in (0, 3, 10, 13):
+        os.remove(base + ec.ToExt(i))
+    rebuilt = ec.rebuild_ec_files(base, [str(other)])
+    assert rebuilt == [0, 3, 10, 13]
+    for i in (0, 3, 10, 13):
+        assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all(), i
+    assert not os.path.exists(base + ".ec05")                 # found elsewhere, not regenerated
+    # too few shards: error before any output file is created (ec_encoder.go:172-175)
+    for i in range(6):
+        os.remove(base + ec.ToExt(i))
+    with pytest.raises(swec.SwecError) as e:
+        ec.rebuild_ec_files(base)
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS" and not os.path.exists(base + ".ec00")
+    # decode side: .ec00-.ec09 → .dat
+    for i in range(10):
+        want[i].tofile(str(tmp_path / ("d.ec%02d" % i)))
+    ec.write_dat_file(str(tmp_path / "d"), size, [str(tmp_path / ("d.ec%02d" % i)) for i in range(10)])
+    assert (np.fromfile(str(tmp_path / "d.dat"), dtype=np.uint8) == dat).all()
+
+
+def test_generate_ec_files_test_parameters_and_fixture(cuda, swec, oracle, kat, tmp_path):
+    """TestEncodingDecoding (ec_test.go:23-47): generateEcFiles("1", 50, 10000, 100) on the fixture volume."""
+    ec = swec.erasure_coding
+    if os.path.exists(REF_DAT):
+        dat = np.fromfile(REF_DAT, dtype=np.uint8)
+    else:
+        dat = oracle.synth(0, 2_590_912, SEED)
+    base = str(tmp_path / "1")
+    dat.tofile(base + ".dat")
+    ec.generateEcFiles(base, 50, 10000, 100)
+    want = oracle.encode_dat_image(dat, buffer_size=50, large=10000, small=100)
+    for i in range(14):
+        assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all(), i
+    if os.path.exists(REF_DAT):
+        digests = [hashlib.sha256(open(base + ec.ToExt(i), "rb").read()).hexdigest() for i in range(14)]
+        assert digests == kat["K8"]["test"]["sha256"]
+    # rebuild with a .vif that carries the ratio (ec_encoder.go:76-95); reference quirk: shards above
+    # 1 MiB must be 1 MiB multiples, these are 259,100 B (< 1 MiB) so one short read is fine
+    open(base + ".vif", "w").write('{\n  "version": 3,\n  "datFileSize": "%d",\n  "ecShardConfig": {\n    "dataShards": 10,\n    "parityShards": 4\n  }\n}\n' % len(dat))
+    os.remove(base + ".ec02")
+    os.remove(base + ".ec12")
+    assert ec.RebuildEcFiles(base) == [2, 12]
+    for i in (2, 12):
+        assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all()
+
+
+def test_custom_ratio_from_vif(cuda, swec, oracle, tmp_path):
+    ec = swec.erasure_coding
+    ctx = ec.ECContext(6, 3)
+    dat = oracle.synth(0, 3_000_001, SEED + 1)
+    base = str(tmp_path / "9")
+    dat.tofile(base + ".dat")
+    ec.generate_ec_files(base, 1024, 1 << 20, 1 << 16, ctx)
+    want = oracle.encode_dat_image(dat, k=6, m=3, buffer_size=1024, large=1 << 20, small=1 << 16)
+    for i in range(9):
+        assert (np.fromfile(base + ctx.ToExt(i), dtype=np.uint8) == want[i]).all(), i
+    open(base + ".vif", "w").write('{"version":3,"ecShardConfig":{"dataShards":6,"parityShards":3}}')
+    os.remove(base + ".ec01")
+    os.remove(base + ".ec08")
+    assert ec.rebuild_ec_files(base) == [1, 8]
+    for i in (1, 8):
+        assert (np.fromfile(base + ctx.ToExt(i), dtype=np.uint8) == want[i]).all()
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs 2-3)
+
+def np_digest(arr):
+    """Same function as swec_digest_kernel: Σ splitmix64(word_j + (j+1)·φ) mod 2^64."""
+    pad = (-len(arr)) % 8
+    w = np.concatenate([arr, np.zeros(pad, dtype=np.uint8)]).view("<u8").astype(np.uint64)
+    with np.errstate(over="ignore"):
+        j = np.arange(len(w), dtype=np.uint64)
+        z = w + (j + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z.sum(dtype=np.uint64))
+
+
+def device_digest(swec, torch, t, nbytes=None):
+    import ctypes as C
+    d = C.c_uint64(0)
+    n = t.numel() if nbytes is None else nbytes
+    rc = swec.lib().swec_digest_device(0, t.data_ptr(), n, C.byref(d), stream(torch))
+    assert rc == 0
+    return d.value
+
+
+def test_synth_and_digest_kernels_match_cpu(cuda, swec, oracle):
+    torch = cuda
+    n = 1 << 20
+    t = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert swec.lib().swec_synth_fill_device(0, t.data_ptr(), 4096, n, SEED, stream(torch)) == 0
+    torch.cuda.synchronize()
+    want = oracle.synth(4096, n, SEED)
+    assert (t.cpu().numpy() == want).all()
+    assert device_digest(swec, torch, t) == np_digest(want)
+    assert device_digest(swec, torch, t, n - 3) == np_digest(want[: n - 3])
+
+
+@pytest.mark.parametrize("dat_size", [30 * (1 << 30), 30000 * (1 << 20) + 123_457])
+def test_full_volume_roundtrip_properties(cuda, swec, oracle, dat_size):
+    """30 GiB (3 large rows) and the 30,000 MiB + ragged default-limit volume (2 large + 952+1 small
+    rows): encode on device; spot-check windows of every parity shard against the oracle; erase 4
+    shards (worst case: all data) → reconstruct → device digests equal the originals."""
+    torch = cuda
+    ec = swec.erasure_coding
+    G, M = 1 << 30, 1 << 20
+    free, _ = torch.cuda.mem_get_info()
+    shard = ec.expected_shard_size(dat_size)
+    if free < dat_size + 9 * shard + (2 << 30):
+        pytest.skip("not enough HBM free")
+    enc = ec.Encoder(10, 4, device=0)
+    s = stream(torch)
+    dat = torch.empty(dat_size + (-dat_size) % 8, dtype=torch.uint8, device="cuda")
+    assert swec.lib().swec_synth_fill_device(0, dat.data_ptr(), 0, dat.numel(), SEED, s) == 0
+    par = [torch.empty(shard, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    enc.encode_volume_device(dat.data_ptr(), dat_size, [p.data_ptr() for p in par], s)
+    torch.cuda.synchronize()
+
+    # windows: start, row boundaries, large→small boundary, ragged end
+    nlarge = dat_size // (10 * G)
+    offs = {0, G - 4096, shard - 4096, (nlarge * G) - 4096 if nlarge else 0, nlarge * G, shard // 2}
+    rem = dat_size - nlarge * 10 * G
+    for off in sorted(o for o in offs if 0 <= o <= shard - 4096):
+        cols = []
+        for i in range(10):   # what .ec0i holds at [off, off+4096)
+            if off < nlarge * G:
+                src = (off // G) * 10 * G + i * G + off % G
+            else:
+                o2 = off - nlarge * G
+                src = nlarge * 10 * G + (o2 // M) * 10 * M + i * M + o2 % M
+            col = np.zeros(4096, dtype=np.uint8)
+            have = max(0, min(4096, dat_size - src))
+            if have:
+                col[:have] = oracle.synth(src, have, SEED)
+            cols.append(col)
+        want = oracle.encode(10, 4, cols)
+        for p in range(4):
+            assert (par[p][off:off + 4096].cpu().numpy() == want[p]).all(), (off, p)
+    par_digest = [device_digest(swec, torch, p) for p in par]
+
+    # worst case: data shards 0-3 erased; rebuild them from 4..13
+    data_sh = [torch.empty(shard, dtype=torch.uint8, device="cuda") for _ in range(10)]
+    for i in range(10):
+        enc.extract_data_shard_device(dat.data_ptr(), dat_size, i, data_sh[i].data_ptr(), s)
+    torch.cuda.synchronize()
+    del dat
+    torch.cuda.empty_cache()
+    want_digest = [device_digest(swec, torch, data_sh[i]) for i in range(4)]
+    for i in range(4):
+        data_sh[i].zero_()
+    allsh = data_sh + par
+    enc.reconstruct_device([t.data_ptr() for t in allsh], [0, 0, 0, 0] + [1] * 10, shard, False, s)
+    torch.cuda.synchronize()
+    assert [device_digest(swec, torch, data_sh[i]) for i in range(4)] == want_digest
+    # parity erased instead: recompute from data, digests must match the first encode
+    for p in par:
+        p.zero_()
+    enc.reconstruct_device([t.data_ptr() for t in allsh], [1] * 10 + [0] * 4, shard, False, s)
+    torch.cuda.synchronize()
+    assert [device_digest(swec, torch, p) for p in par] == par_digest
+    enc.close()
+
+
+def test_linearity_large(cuda, swec):
+    """encode(a) ^ encode(b) == encode(a ^ b) on 1 GiB rows — size-independent property."""
+    torch = cuda
+    enc = swec.erasure_coding.Encoder(10, 4, device=0)
+    n = 1 << 28
+    s = stream(torch)
+    a = torch.empty(10 * n, dtype=torch.uint8, device="cuda")
+    b = torch.empty(10 * n, dtype=torch.uint8, device="cuda")
+    swec.lib().swec_synth_fill_device(0, a.data_ptr(), 0, 10 * n, 1, s)
+    swec.lib().swec_synth_fill_device(0, b.data_ptr(), 0, 10 * n, 2, s)
+    pa = torch.empty(4 * n, dtype=torch.uint8, device="cuda")
+    pb = torch.empty(4 * n, dtype=torch.uint8, device="cuda")
+    pc = torch.empty(4 * n, dtype=torch.uint8, device="cuda")
+
+    def run(x, p):
+        enc.encode_device([x.data_ptr() + i * n for i in range(10)], [p.data_ptr() + j * n for j in range(4)], n, s)
+
+    run(a, pa)
+    run(b, pb)
+    a ^= b
+    run(a, pc)
+    torch.cuda.synchronize()
+    assert torch.equal(pa ^ pb, pc)
+    enc.close()
+
+
+def test_kernel_launch_counter(cuda, swec, enc):
+    before = swec.lib().swec_kernel_launches()
+    shards = [np.zeros(4096, dtype=np.uint8) for _ in range(14)]
+    enc.encode(shards)
+    assert swec.lib().swec_kernel_launches() > before
