@@ -82,8 +82,8 @@ int swec_reconstruct(swec_encoder *enc, uint8_t *const *shards, const uint8_t *p
 /* *ok = 1 iff the parity shards match the data shards.                                         */
 int swec_verify(swec_encoder *enc, uint8_t *const *shards, size_t shard_len, int *ok);
 
-/* ---- the same on DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the
- *      encoder's own stream).  Buffers must stay valid until the stream reaches this point. --- */
+/* ---- the same on DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the CUDA
+ *      default stream).  Buffers must stay valid until the stream reaches this point. --------- */
 int swec_encode_device(swec_encoder *enc, const void *const *data, void *const *parity,
                        size_t shard_len, void *stream);
 int swec_reconstruct_device(swec_encoder *enc, void *const *shards, const uint8_t *present,
@@ -137,6 +137,8 @@ void swec_interval_to_shard(const swec_interval *iv, int64_t large_block, int64_
 
 /* ---- pinned host memory for callers that stage their own buffers ---------------------------- */
 void *swec_alloc_pinned(size_t bytes);
+/* Same, bound to the NUMA node the GPU `device` is attached to (full PCIe rate on 2-socket hosts). */
+void *swec_alloc_pinned_for_device(int device, size_t bytes);
 void swec_free_pinned(void *p);
 
 /* ---- measurement helpers (synthetic volumes, device digests) -------------------------------- */

@@ -22,6 +22,9 @@
 #include <dlfcn.h>
 #include <immintrin.h>
 #include <pthread.h>
+#include <sched.h>
+#include <time.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -260,4 +263,93 @@ int orc_cpu_apply_mt(int kind, int k, int r, const uint8_t *rows, const uint8_t 
     free(tids);
     free(mats);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-box throughput bench: every thread owns its buffers (allocated and first-touched by the
+ * thread itself, so they are NUMA-local), threads are pinned, started together on a barrier and each
+ * runs `passes` passes over its own k inputs → r outputs of `bytes` each.  Returns input GB/s
+ * (1e9) = threads·passes·k·bytes / wall seconds, or a negative value if the kind is unavailable.
+ * This is the CPU's best case: no thread start-up in the timed region, no remote-socket traffic. */
+typedef struct {
+    int kind, k, r, id;
+    const uint8_t *rows;
+    const uint64_t *mats;
+    size_t bytes, batch;
+    int passes;
+    pthread_barrier_t *start, *stop;
+    int ok;
+} bench_job_t;
+
+static void *bench_worker(void *arg)
+{
+    bench_job_t *j = (bench_job_t *)arg;
+    cpu_set_t set;
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    if (ncpu > 0) {
+        CPU_ZERO(&set);
+        CPU_SET((int)(j->id % ncpu), &set);
+        pthread_setaffinity_np(pthread_self(), sizeof set, &set); /* best effort */
+    }
+    uint8_t *in[ORC_MAX_SHARDS], *out[ORC_MAX_SHARDS];
+    j->ok = 1;
+    for (int i = 0; i < j->k; i++) {
+        if (posix_memalign((void **)&in[i], 4096, j->bytes)) { j->ok = 0; in[i] = NULL; continue; }
+        uint64_t s = 0x9E3779B97F4A7C15ull * (uint64_t)(j->id * 64 + i + 1);
+        for (size_t x = 0; x + 8 <= j->bytes; x += 8) { /* xorshift fill = first touch */
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            memcpy(in[i] + x, &s, 8);
+        }
+    }
+    for (int p = 0; p < j->r; p++) {
+        if (posix_memalign((void **)&out[p], 4096, j->bytes)) { j->ok = 0; out[p] = NULL; continue; }
+        memset(out[p], 0, j->bytes);
+    }
+    job_t w = {j->kind, j->k, j->r, j->rows, j->mats, (const uint8_t *const *)in, out, 0, j->bytes, j->batch};
+    if (j->ok) worker(&w); /* warm-up pass */
+    pthread_barrier_wait(j->start);
+    if (j->ok)
+        for (int p = 0; p < j->passes; p++) worker(&w);
+    pthread_barrier_wait(j->stop);
+    for (int i = 0; i < j->k; i++) free(in[i]);
+    for (int p = 0; p < j->r; p++) free(out[p]);
+    return NULL;
+}
+
+double orc_cpu_bench(int kind, int k, int r, const uint8_t *rows, size_t bytes, int threads, int passes,
+                     size_t batch)
+{
+    if (kind == 0 && !g_ref_handle) return -1.0;
+    if (kind == 1 && !orc_cpu_has_gfni()) return -1.0;
+    if (threads < 1) threads = 1;
+    if (batch == 0) batch = 256 * 1024;
+    uint64_t *mats = NULL;
+    if (kind == 1) {
+        mats = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)r * k);
+        for (int i = 0; i < r * k; i++) mats[i] = gfni_matrix(rows[i]);
+    }
+    pthread_barrier_t start, stop;
+    pthread_barrier_init(&start, NULL, (unsigned)threads + 1);
+    pthread_barrier_init(&stop, NULL, (unsigned)threads + 1);
+    bench_job_t *jobs = (bench_job_t *)calloc((size_t)threads, sizeof(bench_job_t));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (bench_job_t){kind, k, r, t, rows, mats, bytes, batch, passes, &start, &stop, 0};
+        pthread_create(&tids[t], NULL, bench_worker, &jobs[t]);
+    }
+    struct timespec t0, t1;
+    pthread_barrier_wait(&start);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_barrier_wait(&stop);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    int ok = 1;
+    for (int t = 0; t < threads; t++) { pthread_join(tids[t], NULL); ok &= jobs[t].ok; }
+    pthread_barrier_destroy(&start);
+    pthread_barrier_destroy(&stop);
+    free(jobs);
+    free(tids);
+    free(mats);
+    if (!ok) return -2.0;
+    double secs = (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
+    return (double)threads * passes * k * (double)bytes / secs / 1e9;
 }

@@ -62,6 +62,9 @@ def lib() -> C.CDLL:
         L.orc_cpu_apply_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_int, C.c_size_t]
 
+        L.orc_cpu_bench.restype = C.c_double
+        L.orc_cpu_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t]
+
         class Interval(C.Structure):
             _fields_ = [("block_index", C.c_int), ("inner_block_offset", C.c_int64),
                         ("size", C.c_int64), ("is_large_block", C.c_int),
@@ -195,3 +198,14 @@ def cpu_apply(kind: int, rows: np.ndarray, inputs: list[np.ndarray], outputs: li
                                 inputs[0].shape[0], threads, batch)
     if rc:
         raise RuntimeError(f"cpu baseline kind {kind} unavailable on this CPU")
+
+
+def cpu_bench(kind: int, rows: np.ndarray, bytes_per_shard: int, threads: int, passes: int,
+              batch: int = 256 * 1024) -> float:
+    """Whole-box CPU throughput (input GB/s): NUMA-local per-thread buffers, pinned threads, barrier
+    start; every thread runs `passes` passes over its own k×bytes_per_shard inputs."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    r, k = rows.shape
+    if kind == 0 and not ref_available():
+        return -1.0
+    return float(lib().orc_cpu_bench(kind, k, r, rows.ctypes.data, bytes_per_shard, threads, passes, batch))

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "swec_interval_to_shard": (None, [C.POINTER(Interval), C.c_int64, C.c_int64, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "swec_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "swec_alloc_pinned_for_device": (C.c_void_p, [C.c_int, C.c_size_t]),
     "swec_free_pinned": (None, [C.c_void_p]),
     "swec_synth_fill_device": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint64, C.c_void_p]),
     "swec_digest_device": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p]),

@@ -55,45 +55,75 @@ __device__ __forceinline__ void swec_stg_stream(u8* p, const uint4& v) {
                  : "memory");
 }
 
-// One thread = one 16-byte column slice of every stream per iteration: K coalesced LDG.128,
-// four independent 32-bit Horner evaluations (ILP), R coalesced STG.128.
-template <class Combiner, bool BLOCKED>
+// One thread = UNROLL 16-byte column slices of every stream per iteration: UNROLL×K coalesced
+// LDG.128 issued back to back (memory-level parallelism), 4×UNROLL independent 32-bit Horner
+// evaluations (ILP), UNROLL×R coalesced STG.128.
+template <class Combiner>
+__device__ __forceinline__ void swec_combine_vec(const uint4 (&d)[Combiner::K], uint4 (&o)[Combiner::R]) {
+    constexpr int K = Combiner::K, R = Combiner::R;
+    u32 x[K], y[R];
+#pragma unroll
+    for (int i = 0; i < K; i++) x[i] = d[i].x;
+    Combiner::combine(x, y);
+#pragma unroll
+    for (int r = 0; r < R; r++) o[r].x = y[r];
+#pragma unroll
+    for (int i = 0; i < K; i++) x[i] = d[i].y;
+    Combiner::combine(x, y);
+#pragma unroll
+    for (int r = 0; r < R; r++) o[r].y = y[r];
+#pragma unroll
+    for (int i = 0; i < K; i++) x[i] = d[i].z;
+    Combiner::combine(x, y);
+#pragma unroll
+    for (int r = 0; r < R; r++) o[r].z = y[r];
+#pragma unroll
+    for (int i = 0; i < K; i++) x[i] = d[i].w;
+    Combiner::combine(x, y);
+#pragma unroll
+    for (int r = 0; r < R; r++) o[r].w = y[r];
+}
+
+template <class Combiner, bool BLOCKED, int UNROLL = 1>
 __device__ __forceinline__ void swec_horner_body(const SwecApplyParams& p) {
     constexpr int K = Combiner::K, R = Combiner::R;
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < p.nvec; v += stride) {
-        const u64 off = v << 4;
-        u64 ioff = off;
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    auto in_offset = [&](u64 vv) -> u64 {
+        u64 ioff = vv << 4;
         if (BLOCKED) {
-            const u64 row = p.block_shift >= 0 ? (v >> p.block_shift) : (v / p.block_vecs);
+            const u64 row = p.block_shift >= 0 ? (vv >> p.block_shift) : (vv / p.block_vecs);
             ioff += row * p.row_extra;
         }
+        return ioff;
+    };
+    if (UNROLL > 1) {
+        for (; v + (UNROLL - 1) * stride < p.nvec; v += UNROLL * stride) {
+            uint4 d[UNROLL][K];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const u64 ioff = in_offset(v + u * stride);
+#pragma unroll
+                for (int i = 0; i < K; i++) d[u][i] = swec_ldg_stream(p.in[i] + ioff);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                uint4 o[R];
+                swec_combine_vec<Combiner>(d[u], o);
+                const u64 off = (v + u * stride) << 4;
+#pragma unroll
+                for (int r = 0; r < R; r++) swec_stg_stream(p.out[r] + off, o[r]);
+            }
+        }
+    }
+    for (; v < p.nvec; v += stride) {
+        const u64 ioff = in_offset(v);
         uint4 d[K];
 #pragma unroll
         for (int i = 0; i < K; i++) d[i] = swec_ldg_stream(p.in[i] + ioff);
         uint4 o[R];
-        u32 x[K], y[R];
+        swec_combine_vec<Combiner>(d, o);
 #pragma unroll
-        for (int i = 0; i < K; i++) x[i] = d[i].x;
-        Combiner::combine(x, y);
-#pragma unroll
-        for (int r = 0; r < R; r++) o[r].x = y[r];
-#pragma unroll
-        for (int i = 0; i < K; i++) x[i] = d[i].y;
-        Combiner::combine(x, y);
-#pragma unroll
-        for (int r = 0; r < R; r++) o[r].y = y[r];
-#pragma unroll
-        for (int i = 0; i < K; i++) x[i] = d[i].z;
-        Combiner::combine(x, y);
-#pragma unroll
-        for (int r = 0; r < R; r++) o[r].z = y[r];
-#pragma unroll
-        for (int i = 0; i < K; i++) x[i] = d[i].w;
-        Combiner::combine(x, y);
-#pragma unroll
-        for (int r = 0; r < R; r++) o[r].w = y[r];
-#pragma unroll
-        for (int r = 0; r < R; r++) swec_stg_stream(p.out[r] + off, o[r]);
+        for (int r = 0; r < R; r++) swec_stg_stream(p.out[r] + (v << 4), o[r]);
     }
 }

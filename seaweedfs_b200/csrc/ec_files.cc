@@ -79,7 +79,8 @@ class FilePipeline {
         const size_t streams = size_t(rows_.cols + rows_.rows);
         slots_.resize(nslots);
         for (auto& s : slots_) {
-            SWEC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.host), streams * chunk_, cudaHostAllocDefault));
+            s.host = static_cast<uint8_t*>(pinned_alloc(enc_->device, streams * chunk_));
+            if (!s.host) return fail(SWEC_ERR_NOMEM, "cannot allocate pinned staging memory");
             SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk_));
             SWEC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             SWEC_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -170,7 +171,7 @@ class FilePipeline {
         cudaSetDevice(enc_->device);
         for (auto& s : slots_) {
             if (s.stream) cudaStreamSynchronize(s.stream);
-            if (s.host) cudaFreeHost(s.host);
+            if (s.host) pinned_free(s.host);
             if (s.dev) cudaFree(s.dev);
             if (s.done) cudaEventDestroy(s.done);
             if (s.stream) cudaStreamDestroy(s.stream);

@@ -31,6 +31,11 @@ int cuda_fail(cudaError_t e, const char* what);
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// pinned host memory on the NUMA node of `device` (plain cudaHostAlloc when that is unknown)
+void* pinned_alloc(int device, size_t bytes);
+void pinned_free(void* p);
+int device_numa_node(int device);
+
 // device-resident multiply tables of one R×K matrix (R ≤ 4)
 struct DeviceTables {
     u32* compact = nullptr;     // [K][2][16]

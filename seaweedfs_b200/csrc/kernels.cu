@@ -28,11 +28,11 @@ std::atomic<unsigned long long> g_kernel_launches{0};
 
 // ------------------------------------------------------------------ RS(10,4) encode, AOT Horner
 
-__global__ void __launch_bounds__(256) rs10x4_encode_flat(const __grid_constant__ SwecApplyParams p) {
-    swec_horner_body<Rs10x4Encode, false>(p);
-}
-__global__ void __launch_bounds__(256) rs10x4_encode_blocked(const __grid_constant__ SwecApplyParams p) {
-    swec_horner_body<Rs10x4Encode, true>(p);
+// Launch shape is a tuning surface (threads per CTA × column slices per thread); the default is the
+// measured best, SWEC_ENC_THREADS / SWEC_ENC_UNROLL select the others for sweeps.
+template <int THREADS, int UNROLL, bool BLOCKED>
+__global__ void __launch_bounds__(THREADS) rs10x4_encode(const __grid_constant__ SwecApplyParams p) {
+    swec_horner_body<Rs10x4Encode, BLOCKED, UNROLL>(p);
 }
 
 // ------------------------------------------------------------------ run-time matrix, smem tables
@@ -229,13 +229,31 @@ int encode_ctas_per_sm() {
     return v;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+template <int THREADS, int UNROLL>
+static cudaError_t launch_rs10x4_shape(const SwecApplyParams& p, bool blocked, int ctas_per_sm, cudaStream_t s) {
+    const unsigned grid = grid_for((p.nvec + UNROLL - 1) / UNROLL, THREADS, ctas_per_sm);
+    if (blocked) rs10x4_encode<THREADS, UNROLL, true><<<grid, THREADS, 0, s>>>(p);
+    else rs10x4_encode<THREADS, UNROLL, false><<<grid, THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStream_t s) {
     if (p.nvec == 0) return cudaSuccess;
-    const unsigned grid = grid_for(p.nvec, 256, encode_ctas_per_sm());
-    if (blocked) rs10x4_encode_blocked<<<grid, 256, 0, s>>>(p);
-    else rs10x4_encode_flat<<<grid, 256, 0, s>>>(p);
+    static const int threads = env_int("SWEC_ENC_THREADS", 256), unroll = env_int("SWEC_ENC_UNROLL", 1);
+    // resident CTAs per SM: 1024 threads' worth unless SWEC_CTAS_PER_SM says otherwise
+    const int c = getenv("SWEC_CTAS_PER_SM") ? encode_ctas_per_sm() : 1024 / (threads == 128 || threads == 512 ? threads : 256);
     g_kernel_launches++;
-    return cudaGetLastError();
+    if (threads == 128 && unroll == 1) return launch_rs10x4_shape<128, 1>(p, blocked, c, s);
+    if (threads == 128 && unroll == 2) return launch_rs10x4_shape<128, 2>(p, blocked, c, s);
+    if (threads == 512 && unroll == 1) return launch_rs10x4_shape<512, 1>(p, blocked, c, s);
+    if (threads == 512 && unroll == 2) return launch_rs10x4_shape<512, 2>(p, blocked, c, s);
+    if (unroll == 2) return launch_rs10x4_shape<256, 2>(p, blocked, c, s);
+    return launch_rs10x4_shape<256, 1>(p, blocked, c, s);
 }
 
 cudaError_t launch_table_apply(const SwecApplyParams& p, const u32* replicated_tables, int K, int r, cudaStream_t s) {

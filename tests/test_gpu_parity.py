@@ -306,10 +306,10 @@ def test_generate_and_rebuild_ec_files(cuda, swec, oracle, tmp_path):
         assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all(), i
     assert not os.path.exists(base + ".ec05")                 # found elsewhere, not regenerated
     # too few shards: error before any output file is created (ec_encoder.go:172-175)
-    for i in range(6):
-        os.remove(base + ec.ToExt(i))
+    for i in (0, 1, 2, 3, 4, 6):
+        os.remove(base + ec.ToExt(i))                         # .ec05 already lives on disk2: 7 left here
     with pytest.raises(swec.SwecError) as e:
-        ec.rebuild_ec_files(base)
+        ec.rebuild_ec_files(base)                             # without additionalDirs: 7 < 10
     assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS" and not os.path.exists(base + ".ec00")
     # decode side: .ec00-.ec09 → .dat
     for i in range(10):
