@@ -341,10 +341,17 @@ def main():
             if dist:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-            # verify one window of host parity against the device-resident result of the same bytes
+            if rank == 0:   # host parity written by the last e2e step vs the oracle on the same host bytes
+                from oracle import pyoracle as po
+                hnp = host.numpy()
+                for off in (0, (n // 2) & ~15, n - 4096):
+                    want = po.encode(10, 4, [hnp[i * n + off:i * n + off + 4096] for i in range(10)])
+                    for p_ in range(4):
+                        assert (hnp[(10 + p_) * n + off:(10 + p_) * n + off + 4096] == want[p_]).all(), "e2e parity mismatch"
             e2e = {"value": round(world * e2e_steps * 10 * n / dt / 1e9, 3), "unit": UNIT,
                    "h2d_bytes_per_step": 10 * n, "d2h_bytes_per_step": 4 * n, "steps": e2e_steps,
-                   "api": "swec_encode (Encoder.Encode) on pinned host shards", "volume_gib": round(10 * n / GIB, 3)}
+                   "api": "swec_encode (Encoder.Encode) on pinned host shards", "volume_gib": round(10 * n / GIB, 3),
+                   "check": "3 windows x 4 host parity shards bit-exact vs oracle"}
             L.swec_free_pinned(raw)
     barrier()
 

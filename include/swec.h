@@ -59,6 +59,9 @@ const char *swec_strerror(int status);
 const char *swec_last_error(void);            /* thread-local detail of the last failure        */
 int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the driver is absent   */
 uint64_t swec_kernel_launches(void);          /* kernels this process has launched (all devices) */
+/* Tuning: "enc_threads" {128,256,512}, "enc_unroll" {1,2}, "ctas_per_sm" (0 = auto),
+ * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "jit_min_bytes".            */
+int swec_set_option(const char *name, long value);
 
 /* ---- encoder = reedsolomon.New(dataShards, parityShards) ----------------------------------- */
 /* device < 0: host-side object only (matrix queries); compute calls then fail with NO_DEVICE.  */

@@ -43,16 +43,32 @@ __device__ __forceinline__ u32 swec_xt1(u32 a, u32 s) {
 #define SWEC_XT0(a) swec_xt1((a), 0u)
 
 // ---- streaming 16-byte global accesses (read-once / write-once data: keep it out of L1) -----
+#ifndef SWEC_LD_POLICY
+#define SWEC_LD_POLICY 0
+#endif
 __device__ __forceinline__ uint4 swec_ldg_stream(const u8* p) {
     uint4 r;
+#if SWEC_LD_POLICY == 1
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];"
+#elif SWEC_LD_POLICY == 2
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+#elif SWEC_LD_POLICY == 3
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];"
+#endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
 }
 __device__ __forceinline__ void swec_stg_stream(u8* p, const uint4& v) {
+#if defined(SWEC_ST_POLICY) && SWEC_ST_POLICY == 1
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+#else
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
+#endif
 }
 
 // One thread = UNROLL 16-byte column slices of every stream per iteration: UNROLL×K coalesced
@@ -87,8 +103,6 @@ __device__ __forceinline__ void swec_combine_vec(const uint4 (&d)[Combiner::K], 
 template <class Combiner, bool BLOCKED, int UNROLL = 1>
 __device__ __forceinline__ void swec_horner_body(const SwecApplyParams& p) {
     constexpr int K = Combiner::K, R = Combiner::R;
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     auto in_offset = [&](u64 vv) -> u64 {
         u64 ioff = vv << 4;
         if (BLOCKED) {
@@ -97,33 +111,33 @@ __device__ __forceinline__ void swec_horner_body(const SwecApplyParams& p) {
         }
         return ioff;
     };
-    if (UNROLL > 1) {
-        for (; v + (UNROLL - 1) * stride < p.nvec; v += UNROLL * stride) {
-            uint4 d[UNROLL][K];
+    // A CTA iteration covers UNROLL*blockDim.x consecutive vectors of every stream (a contiguous
+    // UNROLL*4 KiB run per stream for 256 threads): slice u of thread t is vector base+u*blockDim+t,
+    // so every LDG.128/STG.128 warp instruction is one fully coalesced 512-byte segment.
+    const u64 tile = (u64)blockDim.x * UNROLL;
+    const u64 stride = (u64)gridDim.x * tile;
+    for (u64 base = (u64)blockIdx.x * tile; base < p.nvec; base += stride) {
+        uint4 d[UNROLL][K];
+        bool live[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const u64 ioff = in_offset(v + u * stride);
+        for (int u = 0; u < UNROLL; u++) {
+            const u64 v = base + (u64)u * blockDim.x + threadIdx.x;
+            live[u] = v < p.nvec;
+            if (live[u]) {
+                const u64 ioff = in_offset(v);
 #pragma unroll
                 for (int i = 0; i < K; i++) d[u][i] = swec_ldg_stream(p.in[i] + ioff);
             }
+        }
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
+        for (int u = 0; u < UNROLL; u++) {
+            if (live[u]) {
                 uint4 o[R];
                 swec_combine_vec<Combiner>(d[u], o);
-                const u64 off = (v + u * stride) << 4;
+                const u64 off = (base + (u64)u * blockDim.x + threadIdx.x) << 4;
 #pragma unroll
                 for (int r = 0; r < R; r++) swec_stg_stream(p.out[r] + off, o[r]);
             }
         }
-    }
-    for (; v < p.nvec; v += stride) {
-        const u64 ioff = in_offset(v);
-        uint4 d[K];
-#pragma unroll
-        for (int i = 0; i < K; i++) d[i] = swec_ldg_stream(p.in[i] + ioff);
-        uint4 o[R];
-        swec_combine_vec<Combiner>(d, o);
-#pragma unroll
-        for (int r = 0; r < R; r++) swec_stg_stream(p.out[r] + (v << 4), o[r]);
     }
 }

@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -35,6 +36,10 @@ static size_t env_size(const char* name, size_t dflt) {
     const long long v = atoll(e);
     return v > 0 ? size_t(v) : dflt;
 }
+
+std::atomic<long> g_opt_stage_chunk{long(env_size("SWEC_STAGE_CHUNK", size_t(16) << 20))};
+std::atomic<long> g_opt_stage_slots{long(env_size("SWEC_STAGE_SLOTS", 3))};
+std::atomic<long> g_opt_jit_min_bytes{long(env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20))};
 
 // ------------------------------------------------------------------ NUMA-local pinned host memory
 // PCIe DMA from the far socket costs ~15-20 % of H2D bandwidth on two-socket hosts, so staging
@@ -134,14 +139,18 @@ int swec_encoder_impl::ensure_device() {
 }
 
 int swec_encoder_impl::ensure_slots(size_t chunk) {
-    if (!slots.empty() && slot_chunk >= chunk) return SWEC_OK;
+    const size_t nslots = size_t(std::max(2l, g_opt_stage_slots.load()));
+    if (!slots.empty() && slot_chunk >= chunk && slots.size() == nslots) return SWEC_OK;
     for (auto& s : slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.host) pinned_free(s.host);
         if (s.dev) cudaFree(s.dev);
         s.host = s.dev = nullptr;
     }
-    const size_t nslots = env_size("SWEC_STAGE_SLOTS", 3);
+    for (size_t i = nslots; i < slots.size(); i++) {
+        if (slots[i].done) cudaEventDestroy(slots[i].done);
+        if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
+    }
     slots.resize(nslots);
     const size_t streams = size_t(k) + 2 * size_t(m);
     for (auto& s : slots) {
@@ -248,10 +257,10 @@ int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8
         } else {
             // specialised (NVRTC) Horner kernel when the stream is long enough to pay for the
             // compile, or the kernel is already cached; otherwise shared-memory tables.
-            static const size_t jit_min = env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20);
+            const size_t jit_min = size_t(g_opt_jit_min_bytes.load());
             std::shared_ptr<JitKernel> jk;
             const bool want_jit = R <= SWEC_MAX_OUTPUTS && jit_available() &&
-                                  (jit.count(matrix_key(rows)) || size_t(K) * n >= jit_min);
+                                  (jit_cached(this, rows) || size_t(K) * n >= jit_min);
             if (want_jit) {
                 const int rc = jit_get(this, rows, &jk);
                 if (rc != SWEC_OK && getenv("SWEC_JIT_STRICT")) return rc;
@@ -346,7 +355,7 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
         return SWEC_OK;
     }
 
-    const size_t max_chunk = env_size("SWEC_STAGE_CHUNK", size_t(4) << 20);
+    const size_t max_chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
     const size_t chunk = std::min(max_chunk, (n + 255) & ~size_t(255));
     rc = e->ensure_slots(chunk);
     if (rc) return rc;
@@ -461,6 +470,19 @@ int swec_device_count(int* count) {
 }
 
 uint64_t swec_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int swec_set_option(const char* name, long value) {
+    if (!name) return fail(SWEC_ERR_INVALID_ARG, "NULL option name");
+    const std::string n(name);
+    if (n == "enc_threads" && (value == 128 || value == 256 || value == 512)) g_opt_enc_threads = value;
+    else if (n == "enc_unroll" && (value == 1 || value == 2)) g_opt_enc_unroll = value;
+    else if (n == "ctas_per_sm" && value >= 0 && value <= 64) g_opt_ctas_per_sm = value;
+    else if (n == "stage_chunk" && value >= 4096) g_opt_stage_chunk = (value + 255) & ~255l;
+    else if (n == "stage_slots" && value >= 2 && value <= 16) g_opt_stage_slots = value;
+    else if (n == "jit_min_bytes" && value >= 0) g_opt_jit_min_bytes = value;
+    else return fail(SWEC_ERR_INVALID_ARG, "unknown option or value out of range: " + n);
+    return SWEC_OK;
+}
 
 int swec_encoder_new(int k, int m, int device, swec_encoder** out) {
     if (!out) return fail(SWEC_ERR_INVALID_ARG, "out is NULL");

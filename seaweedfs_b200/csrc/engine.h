@@ -85,6 +85,7 @@ struct swec_encoder_impl {
 bool jit_available();
 // Specialised Horner kernel for `rows` on the current device (compiled once per matrix/process).
 int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out);
+bool jit_cached(swec_encoder_impl* enc, const Matrix& rows);
 cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocked, cudaStream_t s);
 
 }  // namespace swec

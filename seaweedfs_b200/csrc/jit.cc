@@ -27,6 +27,7 @@ static const char kDeviceCommonSrc[] =
     ;
 
 struct JitKernel {
+    int threads = 256, unroll = 1;  // launch shape the kernel was specialised for
     cudaLibrary_t lib = nullptr;
     cudaKernel_t flat = nullptr, blocked = nullptr;
     CodegenStats stats;
@@ -79,9 +80,19 @@ std::map<std::vector<uint8_t>, std::shared_ptr<JitKernel>> g_jit_cache;  // proc
 
 bool jit_available() { return nvrtc().ok; }
 
-int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out) {
-    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols)};
+static std::vector<uint8_t> jit_key(const Matrix& rows, int threads, int unroll) {
+    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols), uint8_t(threads / 64), uint8_t(unroll)};
     key.insert(key.end(), rows.v.begin(), rows.v.end());
+    return key;
+}
+
+bool jit_cached(swec_encoder_impl* enc, const Matrix& rows) {
+    return enc->jit.count(jit_key(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()))) != 0;
+}
+
+int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out) {
+    const int threads = int(g_opt_enc_threads.load()), unroll = int(g_opt_enc_unroll.load());
+    const std::vector<uint8_t> key = jit_key(rows, threads, unroll);
     auto local = enc->jit.find(key);
     if (local != enc->jit.end()) {
         *out = local->second;
@@ -99,14 +110,17 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
     if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
 
     auto kernel = std::make_shared<JitKernel>();
+    kernel->threads = threads;
+    kernel->unroll = unroll;
+    const std::string T = std::to_string(threads), U = std::to_string(unroll);
     std::string src = "#define SWEC_XT_VARIANT 0\n";
     src += kDeviceCommonSrc;
     src += generate_combine(rows, "SwecJit", CodegenOptions{}, &kernel->stats);
     src +=
-        "extern \"C\" __global__ void __launch_bounds__(256) swec_jit_flat(const __grid_constant__ SwecApplyParams p) {\n"
-        "    swec_horner_body<SwecJit, false>(p);\n}\n"
-        "extern \"C\" __global__ void __launch_bounds__(256) swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
-        "    swec_horner_body<SwecJit, true>(p);\n}\n";
+        "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_flat(const __grid_constant__ SwecApplyParams p) {\n"
+        "    swec_horner_body<SwecJit, false, " + U + ">(p);\n}\n"
+        "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
+        "    swec_horner_body<SwecJit, true, " + U + ">(p);\n}\n";
 
     nvrtcProgram prog = nullptr;
     if (n.create(&prog, src.c_str(), "swec_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
@@ -149,12 +163,14 @@ cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocke
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const u64 need = (p.nvec + 255) / 256;
+    const u64 per_cta = u64(k.threads) * u64(k.unroll);
+    const u64 need = (p.nvec + per_cta - 1) / per_cta;
     const u64 cap = u64(sms) * u64(encode_ctas_per_sm());
     const unsigned grid = unsigned(need < cap ? need : cap);
     void* args[] = {const_cast<SwecApplyParams*>(&p)};
     g_kernel_launches++;
-    return cudaLaunchKernel(reinterpret_cast<const void*>(blocked ? k.blocked : k.flat), dim3(grid), dim3(256), args, 0, s);
+    return cudaLaunchKernel(reinterpret_cast<const void*>(blocked ? k.blocked : k.flat), dim3(grid),
+                            dim3(unsigned(k.threads)), args, 0, s);
 }
 
 }  // namespace swec

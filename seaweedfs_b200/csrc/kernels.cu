@@ -12,6 +12,7 @@
 //   swec_compare_kernel           count of differing 16-byte vectors (parity verify / scrub)
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 
@@ -220,18 +221,23 @@ static unsigned grid_for(u64 items, int threads, int ctas_per_sm) {
     return (unsigned)(need < cap ? (need ? need : 1) : cap);
 }
 
-int encode_ctas_per_sm() {
-    static const int v = [] {
-        const char* e = getenv("SWEC_CTAS_PER_SM");
-        const int n = e ? atoi(e) : 0;
-        return n > 0 && n <= 64 ? n : 4;
-    }();
-    return v;
-}
-
-static int env_int(const char* name, int dflt) {
+// ---- tuning options (defaults = measured best); env at start-up, swec_set_option later
+static long env_long(const char* name, long dflt) {
     const char* e = getenv(name);
-    return e && *e ? atoi(e) : dflt;
+    return e && *e ? atol(e) : dflt;
+}
+std::atomic<long> g_opt_enc_threads{env_long("SWEC_ENC_THREADS", 512)};
+std::atomic<long> g_opt_enc_unroll{env_long("SWEC_ENC_UNROLL", 2)};
+std::atomic<long> g_opt_ctas_per_sm{env_long("SWEC_CTAS_PER_SM", 0)};  // 0 = derive from the shape
+
+int encode_ctas_per_sm() {
+    const long c = g_opt_ctas_per_sm.load();
+    if (c > 0 && c <= 64) return int(c);
+    const long t = g_opt_enc_threads.load(), u = g_opt_enc_unroll.load();
+    // measured best (profiles/r01e_policy_shape_sweep.jsonl): ≈768 resident threads per SM with one
+    // column slice per thread, ≈512 with two — more warps only add DRAM page conflicts
+    const long tt = t == 128 || t == 512 ? t : 256;
+    return int(std::max(1l, (u > 1 ? 512 : 768) / tt));
 }
 
 template <int THREADS, int UNROLL>
@@ -244,9 +250,8 @@ static cudaError_t launch_rs10x4_shape(const SwecApplyParams& p, bool blocked, i
 
 cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStream_t s) {
     if (p.nvec == 0) return cudaSuccess;
-    static const int threads = env_int("SWEC_ENC_THREADS", 256), unroll = env_int("SWEC_ENC_UNROLL", 1);
-    // resident CTAs per SM: 1024 threads' worth unless SWEC_CTAS_PER_SM says otherwise
-    const int c = getenv("SWEC_CTAS_PER_SM") ? encode_ctas_per_sm() : 1024 / (threads == 128 || threads == 512 ? threads : 256);
+    const long threads = g_opt_enc_threads.load(), unroll = g_opt_enc_unroll.load();
+    const int c = encode_ctas_per_sm();
     g_kernel_launches++;
     if (threads == 128 && unroll == 1) return launch_rs10x4_shape<128, 1>(p, blocked, c, s);
     if (threads == 128 && unroll == 2) return launch_rs10x4_shape<128, 2>(p, blocked, c, s);

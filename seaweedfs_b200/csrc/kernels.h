@@ -10,7 +10,9 @@ namespace swec {
 
 extern std::atomic<unsigned long long> g_kernel_launches;
 
-// tuning knob (resident CTAs per SM the persistent grids are sized for); SWEC_CTAS_PER_SM overrides
+// tuning knobs: launch shape of the Horner kernels (swec_set_option / SWEC_ENC_THREADS, SWEC_ENC_UNROLL,
+// SWEC_CTAS_PER_SM).  ctas_per_sm = resident CTAs per SM the persistent grids are sized for.
+extern std::atomic<long> g_opt_enc_threads, g_opt_enc_unroll, g_opt_ctas_per_sm;
 int encode_ctas_per_sm();
 
 cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStream_t s);
