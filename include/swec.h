@@ -60,8 +60,14 @@ const char *swec_last_error(void);            /* thread-local detail of the last
 int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the driver is absent   */
 uint64_t swec_kernel_launches(void);          /* kernels this process has launched (all devices) */
 /* Tuning: "enc_threads" {128,256,512}, "enc_unroll" {1,2}, "ctas_per_sm" (0 = auto),
- * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "jit_min_bytes".            */
+ * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "jit" {0,1},
+ * "jit_min_bytes" (streams at least this long compile their kernel inline, shorter ones in the
+ * background).                                                                                   */
 int swec_set_option(const char *name, long value);
+/* Diagnostics: generate and NVRTC-compile (sm_100a) the specialised kernel for an r×k matrix without
+ * loading it — needs no GPU.  Reports the cubin size and the generator's instruction statistics.  */
+int swec_debug_jit_compile(int r, int k, const uint8_t *rows, size_t *cubin_bytes, int *xtime_steps,
+                           int *xor_ops);
 
 /* ---- encoder = reedsolomon.New(dataShards, parityShards) ----------------------------------- */
 /* device < 0: host-side object only (matrix queries); compute calls then fail with NO_DEVICE.  */

@@ -38,6 +38,8 @@ PROTOTYPES = {
     "swec_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "swec_kernel_launches": (C.c_uint64, []),
     "swec_set_option": (C.c_int, [C.c_char_p, C.c_long]),
+    "swec_debug_jit_compile": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int)]),
     "swec_encoder_new": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "swec_encoder_free": (None, [C.c_void_p]),
     "swec_encoder_matrix": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -39,6 +39,7 @@ static size_t env_size(const char* name, size_t dflt) {
 
 std::atomic<long> g_opt_stage_chunk{long(env_size("SWEC_STAGE_CHUNK", size_t(16) << 20))};
 std::atomic<long> g_opt_stage_slots{long(env_size("SWEC_STAGE_SLOTS", 3))};
+std::atomic<long> g_opt_jit_enabled{1};
 std::atomic<long> g_opt_jit_min_bytes{long(env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20))};
 
 // ------------------------------------------------------------------ NUMA-local pinned host memory
@@ -257,12 +258,14 @@ int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8
         } else {
             // specialised (NVRTC) Horner kernel when the stream is long enough to pay for the
             // compile, or the kernel is already cached; otherwise shared-memory tables.
+            // Long streams compile the specialised kernel inline (≈0.3 s, amortised); short ones start
+            // the compile in the background, are served from the table kernel meanwhile, and pick the
+            // fast kernel up once it is ready (degraded reads repeat the same few matrices).
             const size_t jit_min = size_t(g_opt_jit_min_bytes.load());
             std::shared_ptr<JitKernel> jk;
-            const bool want_jit = R <= SWEC_MAX_OUTPUTS && jit_available() &&
-                                  (jit_cached(this, rows) || size_t(K) * n >= jit_min);
-            if (want_jit) {
-                const int rc = jit_get(this, rows, &jk);
+            if (R <= SWEC_MAX_OUTPUTS && g_opt_jit_enabled.load() && jit_available()) {
+                const bool wait = size_t(K) * n >= jit_min || layout.blocked;
+                const int rc = jit_get(this, rows, &jk, wait);
                 if (rc != SWEC_OK && getenv("SWEC_JIT_STRICT")) return rc;
             }
             if (jk) {
@@ -471,6 +474,13 @@ int swec_device_count(int* count) {
 
 uint64_t swec_kernel_launches(void) { return g_kernel_launches.load(); }
 
+int swec_debug_jit_compile(int r, int k, const uint8_t* rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
+    if (r <= 0 || k <= 0 || k > SWEC_MAX_INPUTS || !rows) return fail(SWEC_ERR_INVALID_ARG, "bad matrix");
+    Matrix m(r, k);
+    memcpy(m.v.data(), rows, m.v.size());
+    return jit_debug_compile(m, cubin_bytes, xtime_steps, xor_ops);
+}
+
 int swec_set_option(const char* name, long value) {
     if (!name) return fail(SWEC_ERR_INVALID_ARG, "NULL option name");
     const std::string n(name);
@@ -480,6 +490,7 @@ int swec_set_option(const char* name, long value) {
     else if (n == "stage_chunk" && value >= 4096) g_opt_stage_chunk = (value + 255) & ~255l;
     else if (n == "stage_slots" && value >= 2 && value <= 16) g_opt_stage_slots = value;
     else if (n == "jit_min_bytes" && value >= 0) g_opt_jit_min_bytes = value;
+    else if (n == "jit" && (value == 0 || value == 1)) g_opt_jit_enabled = value;
     else return fail(SWEC_ERR_INVALID_ARG, "unknown option or value out of range: " + n);
     return SWEC_OK;
 }
@@ -623,7 +634,7 @@ int swec_encode_volume_device(swec_encoder* e, const void* dat_v, int64_t dat_si
     cudaStream_t s = pick_stream(e, stream);
     const Matrix rows = parity_rows(e);
     bool horner = is_rs10x4_parity(*e, rows);
-    if (!horner && e->m <= SWEC_MAX_OUTPUTS && jit_available()) {
+    if (!horner && e->m <= SWEC_MAX_OUTPUTS && g_opt_jit_enabled.load() && jit_available()) {
         std::shared_ptr<JitKernel> jk;
         horner = jit_get(e, rows, &jk) == SWEC_OK;
     }

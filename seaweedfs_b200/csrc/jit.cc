@@ -14,8 +14,10 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 
 #include "codegen.h"
 #include "engine.h"
@@ -73,8 +75,13 @@ Nvrtc& nvrtc() {
     return n;
 }
 
+struct JitEntry {
+    enum State { kCompiling, kReady, kFailed } state = kCompiling;
+    std::shared_ptr<JitKernel> kernel;
+};
 std::mutex g_jit_mu;
-std::map<std::vector<uint8_t>, std::shared_ptr<JitKernel>> g_jit_cache;  // process-wide
+std::condition_variable g_jit_cv;
+std::map<std::vector<uint8_t>, JitEntry> g_jit_cache;  // process-wide
 
 }  // namespace
 
@@ -90,7 +97,60 @@ bool jit_cached(swec_encoder_impl* enc, const Matrix& rows) {
     return enc->jit.count(jit_key(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()))) != 0;
 }
 
-int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out) {
+// generate + NVRTC-compile the specialised kernels for `rows`; no CUDA context needed
+static int compile_cubin(const Matrix& rows, int threads, int unroll, std::vector<char>* cubin, CodegenStats* stats) {
+    Nvrtc& n = nvrtc();
+    if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
+    if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
+    const std::string T = std::to_string(threads), U = std::to_string(unroll);
+    std::string src = "#define SWEC_XT_VARIANT 0\n";
+    src += kDeviceCommonSrc;
+    src += generate_combine(rows, "SwecJit", CodegenOptions{}, stats);
+    src +=
+        "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_flat(const __grid_constant__ SwecApplyParams p) {\n"
+        "    swec_horner_body<SwecJit, false, " + U + ">(p);\n}\n"
+        "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
+        "    swec_horner_body<SwecJit, true, " + U + ">(p);\n}\n";
+    nvrtcProgram prog = nullptr;
+    if (n.create(&prog, src.c_str(), "swec_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(SWEC_ERR_JIT, "nvrtcCreateProgram failed");
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    if (n.compile(prog, 3, opts) != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        n.log_size(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) n.log(prog, &log[0]);
+        n.destroy(&prog);
+        return fail(SWEC_ERR_JIT, "NVRTC compile failed: " + log);
+    }
+    size_t cs = 0;
+    n.cubin_size(prog, &cs);
+    cubin->resize(cs);
+    n.cubin(prog, cubin->data());
+    n.destroy(&prog);
+    return SWEC_OK;
+}
+
+static std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll) {
+    auto kernel = std::make_shared<JitKernel>();
+    kernel->threads = threads;
+    kernel->unroll = unroll;
+    std::vector<char> cubin;
+    if (compile_cubin(rows, threads, unroll, &cubin, &kernel->stats) != SWEC_OK) return nullptr;
+    cudaError_t e = cudaLibraryLoadData(&kernel->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->flat, kernel->lib, "swec_jit_flat");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->blocked, kernel->lib, "swec_jit_blocked");
+    if (e != cudaSuccess) {
+        cuda_fail(e, "loading the specialised kernel");
+        return nullptr;
+    }
+    return kernel;
+}
+
+// Cache entry states: absent → (compiling) → ready | failed.  wait = true compiles inline (long
+// streams: the ≈0.3 s is amortised); wait = false starts a background compile and reports "not
+// ready" so the caller serves this call from the table kernel and later calls from the fast one.
+int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait) {
     const int threads = int(g_opt_enc_threads.load()), unroll = int(g_opt_enc_unroll.load());
     const std::vector<uint8_t> key = jit_key(rows, threads, unroll);
     auto local = enc->jit.find(key);
@@ -98,64 +158,57 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
         *out = local->second;
         return SWEC_OK;
     }
-    std::lock_guard<std::mutex> lock(g_jit_mu);
-    auto it = g_jit_cache.find(key);
-    if (it != g_jit_cache.end()) {
-        enc->jit[key] = it->second;
-        *out = it->second;
-        return it->second ? SWEC_OK : SWEC_ERR_JIT;
+    if (!nvrtc().ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
+    std::unique_lock<std::mutex> lock(g_jit_mu);
+    for (;;) {
+        auto it = g_jit_cache.find(key);
+        if (it == g_jit_cache.end()) break;
+        if (it->second.state == JitEntry::kCompiling) {
+            if (!wait) {
+                *out = nullptr;
+                return SWEC_OK;
+            }
+            g_jit_cv.wait(lock);
+            continue;
+        }
+        enc->jit[key] = it->second.kernel;  // ready or failed (nullptr): remember either way
+        *out = it->second.kernel;
+        return it->second.kernel ? SWEC_OK : SWEC_ERR_JIT;
     }
-    Nvrtc& n = nvrtc();
-    if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
-    if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
+    g_jit_cache[key].state = JitEntry::kCompiling;
+    if (!wait) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::thread([rows, key, threads, unroll, dev] {
+            cudaSetDevice(dev);
+            auto k = build_kernel(rows, threads, unroll);
+            std::lock_guard<std::mutex> lk(g_jit_mu);
+            g_jit_cache[key].kernel = k;
+            g_jit_cache[key].state = k ? JitEntry::kReady : JitEntry::kFailed;
+            g_jit_cv.notify_all();
+        }).detach();
+        *out = nullptr;
+        return SWEC_OK;
+    }
+    lock.unlock();
+    auto k = build_kernel(rows, threads, unroll);
+    lock.lock();
+    g_jit_cache[key].kernel = k;
+    g_jit_cache[key].state = k ? JitEntry::kReady : JitEntry::kFailed;
+    g_jit_cv.notify_all();
+    enc->jit[key] = k;
+    *out = k;
+    return k ? SWEC_OK : SWEC_ERR_JIT;
+}
 
-    auto kernel = std::make_shared<JitKernel>();
-    kernel->threads = threads;
-    kernel->unroll = unroll;
-    const std::string T = std::to_string(threads), U = std::to_string(unroll);
-    std::string src = "#define SWEC_XT_VARIANT 0\n";
-    src += kDeviceCommonSrc;
-    src += generate_combine(rows, "SwecJit", CodegenOptions{}, &kernel->stats);
-    src +=
-        "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_flat(const __grid_constant__ SwecApplyParams p) {\n"
-        "    swec_horner_body<SwecJit, false, " + U + ">(p);\n}\n"
-        "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
-        "    swec_horner_body<SwecJit, true, " + U + ">(p);\n}\n";
-
-    nvrtcProgram prog = nullptr;
-    if (n.create(&prog, src.c_str(), "swec_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
-        g_jit_cache[key] = nullptr;
-        return fail(SWEC_ERR_JIT, "nvrtcCreateProgram failed");
-    }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-    const nvrtcResult cr = n.compile(prog, 3, opts);
-    if (cr != NVRTC_SUCCESS) {
-        size_t ls = 0;
-        n.log_size(prog, &ls);
-        std::string log(ls, '\0');
-        if (ls) n.log(prog, &log[0]);
-        n.destroy(&prog);
-        g_jit_cache[key] = nullptr;
-        return fail(SWEC_ERR_JIT, "NVRTC compile failed: " + log);
-    }
-    size_t cs = 0;
-    n.cubin_size(prog, &cs);
-    std::vector<char> cubin(cs);
-    n.cubin(prog, cubin.data());
-    n.destroy(&prog);
-
-    cudaError_t e = cudaLibraryLoadData(&kernel->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->flat, kernel->lib, "swec_jit_flat");
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->blocked, kernel->lib, "swec_jit_blocked");
-    if (e != cudaSuccess) {
-        g_jit_cache[key] = nullptr;
-        cuda_fail(e, "loading the specialised kernel");
-        return SWEC_ERR_JIT;
-    }
-    g_jit_cache[key] = kernel;
-    enc->jit[key] = kernel;
-    *out = kernel;
-    return SWEC_OK;
+int jit_debug_compile(const Matrix& rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
+    std::vector<char> cubin;
+    CodegenStats st;
+    const int rc = compile_cubin(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()), &cubin, &st);
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (xtime_steps) *xtime_steps = st.xtime_steps;
+    if (xor_ops) *xor_ops = st.xor_ops;
+    return rc;
 }
 
 cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocked, cudaStream_t s) {

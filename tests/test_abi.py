@@ -169,3 +169,26 @@ def test_write_dat_file_roundtrip(swec, oracle, tmp_path):
         shards[i].tofile(names[-1])
     ec.write_dat_file(str(tmp_path / "out"), len(dat), names, 10, 10000, 100)
     assert (np.fromfile(str(tmp_path / "out.dat"), dtype=np.uint8) == dat).all()
+
+
+def test_jit_source_compiles_for_sm100a_without_gpu(swec):
+    """The run-time specialised kernel source (prelude + generated combiner) goes through NVRTC for
+    sm_100a on the CPU box: catches generator / prelude errors before any GPU time is spent."""
+    import time
+    from oracle import rs_numpy as rn
+    L = swec.lib()
+    cases = [rn.fused_reconstruct_rows(10, 4, [i not in e for i in range(14)])[2]
+             for e in ((0, 1, 2, 3), (5,), (2, 11), (10, 11, 12, 13))]
+    cases.append(rn.build_matrix(6, 9)[6:])
+    cases.append(rn.build_matrix(20, 28)[20:])          # 8 output rows: the per-launch maximum
+    for rows in cases:
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        size, steps, xors = C.c_size_t(0), C.c_int(0), C.c_int(0)
+        t0 = time.perf_counter()
+        rc = L.swec_debug_jit_compile(rows.shape[0], rows.shape[1], rows.ctypes.data, C.byref(size),
+                                      C.byref(steps), C.byref(xors))
+        if rc == -8 and b"not available" in L.swec_last_error():
+            pytest.skip("NVRTC not installed here")
+        assert rc == 0, L.swec_last_error()
+        assert size.value > 1000 and steps.value <= 7 * rows.shape[0]
+        print(rows.shape, size.value, steps.value, xors.value, round(time.perf_counter() - t0, 3))

@@ -166,24 +166,40 @@ def test_reconstruct_degraded_read_pattern(cuda, swec, oracle):
         assert (bufs[p] == full[p]).all()
 
 
-def test_reconstruct_device_jit_and_tables_agree(cuda, swec, oracle, monkeypatch):
-    """Both run-time-matrix kernels (NVRTC-specialised Horner, shared-memory tables) against the oracle."""
+def test_reconstruct_device_jit_and_tables_agree(cuda, swec, oracle):
+    """Both run-time-matrix kernels (NVRTC-specialised Horner, shared-memory tables) against the oracle,
+    plus the hand-over: short streams start on tables while the kernel compiles in the background."""
     torch = cuda
+    L = swec.lib()
     n = 1 << 20
     rng = np.random.default_rng(8)
     data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
     full = data + oracle.encode(10, 4, data)
-    for min_bytes in ("1", str(1 << 40)):                    # force JIT / force tables
-        monkeypatch.setenv("SWEC_JIT_MIN_BYTES", min_bytes)
-        for erased in [(0, 1, 2, 3), (2, 11), (10, 13), (4, 5, 6, 12)]:
-            enc = swec.erasure_coding.Encoder(10, 4, device=0)
-            t = [dev(torch, s) if i not in erased else torch.zeros(n, dtype=torch.uint8, device="cuda")
-                 for i, s in enumerate(full)]
-            enc.reconstruct_device([x.data_ptr() for x in t], [i not in erased for i in range(14)], n, False, stream(torch))
-            torch.cuda.synchronize()
-            for i in erased:
-                assert (t[i].cpu().numpy() == full[i]).all(), (min_bytes, erased, i)
-            enc.close()
+
+    def run(erased, enc):
+        t = [dev(torch, s) if i not in erased else torch.zeros(n, dtype=torch.uint8, device="cuda")
+             for i, s in enumerate(full)]
+        enc.reconstruct_device([x.data_ptr() for x in t], [i not in erased for i in range(14)], n, False, stream(torch))
+        torch.cuda.synchronize()
+        for i in erased:
+            assert (t[i].cpu().numpy() == full[i]).all(), (erased, i)
+
+    try:
+        for jit, min_bytes in ((1, 1), (0, 1), (1, 1 << 40)):      # inline JIT / tables only / background JIT
+            assert L.swec_set_option(b"jit", jit) == 0 and L.swec_set_option(b"jit_min_bytes", min_bytes) == 0
+            for erased in [(0, 1, 2, 3), (2, 11), (10, 13), (4, 5, 6, 12), (1, 7, 9)]:
+                enc = swec.erasure_coding.Encoder(10, 4, device=0)
+                before = L.swec_kernel_launches()
+                run(erased, enc)
+                if min_bytes > 1 and jit:
+                    import time
+                    time.sleep(1.0)                                 # let the background compile land
+                    run(erased, enc)                                # now served by the specialised kernel
+                assert L.swec_kernel_launches() > before
+                enc.close()
+    finally:
+        L.swec_set_option(b"jit", 1)
+        L.swec_set_option(b"jit_min_bytes", 64 << 20)
 
 
 def test_reconstruct_errors(cuda, enc):
