@@ -34,6 +34,17 @@ METRIC = "rs10_4_encode_input_GBps"
 UNIT = "GB/s"
 
 
+def load_traffic(dat_size):
+    """dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/), scaled
+    to this run's volume if it differs; None when no capture is on record."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return int((t["dram_bytes_read"] + t["dram_bytes_write"]) * (dat_size / t["dat_bytes"])), t["source"]
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -363,6 +374,7 @@ def main():
         algo_bytes = 1.4 * dat_size                              # read 10 streams once, write 4
         achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
         clocks = clk.summary()
+        traffic, traffic_src = load_traffic(dat_size)
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
@@ -373,7 +385,8 @@ def main():
                        "l2": "inputs (30 GiB) far exceed the 126 MB L2; no flush needed",
                        "seed": hex(SEED0), "check": checked},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": "rs10x4_encode_blocked", "algorithmic_bytes_per_launch": int(algo_bytes),
                          "kernel_ms": round(kernel_ms, 4)},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "reconstruct": recon,
