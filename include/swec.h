@@ -17,6 +17,8 @@
  *   swec_verify                 (Rust twin) rs.verify     seaweed-volume/src/storage/erasure_coding/ec_encoder.rs:177-278
  *   swec_write_ec_files         WriteEcFiles / generateEcFiles   ec_encoder.go:61-69,110-128
  *   swec_rebuild_ec_files       RebuildEcFiles / generateMissingEcFiles   ec_encoder.go:74-104,146-200
+ *   swec_verify_ec_files        (Rust twin) verify_ec_shards   seaweed-volume/src/storage/erasure_coding/ec_encoder.rs:177-278
+ *   swec_reconstruct_batch      batched ReconstructData   weed/storage/store_ec.go:482-560 (one call per interval today)
  *   swec_write_dat_file         WriteDatFile              weed/storage/erasure_coding/ec_decoder.go:176-223
  *   swec_locate_data            LocateData                weed/storage/erasure_coding/ec_locate.go:16-53
  *   swec_expected_shard_size    calculateExpectedShardSize   weed/storage/disk_location_ec.go:428-448
@@ -88,6 +90,16 @@ int swec_encode(swec_encoder *enc, uint8_t *const *shards, size_t shard_len);
  * only indices < k (ReconstructData).  All present ⇒ no-op; fewer than k ⇒ TOO_FEW_SHARDS.     */
 int swec_reconstruct(swec_encoder *enc, uint8_t *const *shards, const uint8_t *present,
                      size_t shard_len, int data_only);
+/* Many ReconstructData/Reconstruct calls at once — the batched form of the degraded-read path
+ * (store_ec.go:482-560 issues one tiny call per needle interval).  Items that share a presence
+ * mask are packed into common launches; results are identical to calling swec_reconstruct on each. */
+typedef struct swec_reconstruct_item {
+    uint8_t *const *shards;   /* k+m pointers, as for swec_reconstruct */
+    const uint8_t *present;   /* k+m flags */
+    size_t shard_len;
+    int data_only;
+} swec_reconstruct_item;
+int swec_reconstruct_batch(swec_encoder *enc, const swec_reconstruct_item *items, int n_items);
 /* *ok = 1 iff the parity shards match the data shards.                                         */
 int swec_verify(swec_encoder *enc, uint8_t *const *shards, size_t shard_len, int *ok);
 
@@ -97,6 +109,10 @@ int swec_encode_device(swec_encoder *enc, const void *const *data, void *const *
                        size_t shard_len, void *stream);
 int swec_reconstruct_device(swec_encoder *enc, void *const *shards, const uint8_t *present,
                             size_t shard_len, int data_only, void *stream);
+/* The primitive underneath: out[p][x] = XOR_i rows[p*k+i] ⊗ in[i][x] for any r×k matrix over
+ * GF(2^8)/0x11D (k ≤ 32) — what code_some_slices does (reed-solomon-erasure core.rs:484-512).    */
+int swec_apply_device(swec_encoder *enc, int r, int k, const uint8_t *rows, const void *const *in,
+                      void *const *out, size_t shard_len, void *stream);
 /* A whole volume image resident in HBM → parity shard images, following the two-tier striping
  * of encodeDatFile (ec_encoder.go:280-321): rows of k large blocks while ≥ k*large bytes
  * remain, then rows of k small blocks, the last one zero-padded.  parity[p] receives
@@ -123,6 +139,13 @@ int swec_generate_ec_files(const char *base_file_name, int64_t buffer_size, int6
 int swec_rebuild_ec_files(const char *base_file_name, const char *const *additional_dirs,
                           int n_additional_dirs, int data_shards, int parity_shards, int device,
                           uint32_t *rebuilt, int *n_rebuilt);
+/* Scrub: re-encode .ec00–.ec(k-1) on the GPU and compare with the parity shards on disk (the Rust
+ * twin's verify_ec_shards, seaweed-volume/src/storage/erasure_coding/ec_encoder.rs:177-278; the Go
+ * scrub never checks parity, ec_volume_scrub.go:27-118).  mismatched_vectors[p] (m entries, may be
+ * NULL) = number of differing 16-byte vectors in parity shard p; *ok = 1 iff all are zero.       */
+int swec_verify_ec_files(const char *base_file_name, const char *const *additional_dirs,
+                         int n_additional_dirs, int data_shards, int parity_shards, int device,
+                         uint64_t *mismatched_vectors, int *ok);
 int swec_write_dat_file(const char *base_file_name, int64_t dat_file_size,
                         const char *const *shard_file_names, int data_shards,
                         int64_t large_block, int64_t small_block);

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--reconstruct", action="store_true")
     ap.add_argument("--best", action="store_true", help="only the leading shapes, three repeats each")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--memprobe", action="store_true",
+                    help="memory-pipeline ceiling: the same kernel body with a trivial (all-ones) matrix, and a D2D copy")
     args = ap.parse_args()
     import torch
     import seaweedfs_b200
@@ -63,6 +65,26 @@ def main():
         print(json.dumps({"tag": args.tag, "kernel": "rs10x4_encode", "threads": t, "unroll": u, "ctas_per_sm": c,
                           "ms": round(ms, 4), "input_GBps": round(size / ms / 1e6, 1),
                           "frac": round(1.4 * size / ms / 1e6 / peak, 4)}), flush=True)
+    if args.memprobe:
+        import numpy as np
+        S = shard & ~15
+        d = [dat.data_ptr() + i * S for i in range(10)]
+        L.swec_set_option(b"jit_min_bytes", 1)
+        for t, u, c in ((512, 2, 1), (256, 1, 3)):
+            L.swec_set_option(b"enc_threads", t)
+            L.swec_set_option(b"enc_unroll", u)
+            L.swec_set_option(b"ctas_per_sm", c)
+            e3 = ec.Encoder(10, 4, device=0)
+            ones = np.ones((4, 10), dtype=np.uint8)
+            ms = timed(lambda: e3.apply_device(ones, d, pp, S, stream))
+            print(json.dumps({"kernel": "xor_all_10_to_4 (no GF work)", "threads": t, "unroll": u, "ctas_per_sm": c,
+                              "ms": round(ms, 4), "frac": round(14 * S / ms / 1e6 / peak, 4)}), flush=True)
+        a = dat[: 12 << 30]
+        b = torch.empty(12 << 30, dtype=torch.uint8, device="cuda")
+        ms = timed(lambda: b.copy_(a))
+        print(json.dumps({"kernel": "torch copy 12 GiB", "ms": round(ms, 4), "GBps_rw": round(2 * (12 << 30) / ms / 1e6, 1)}), flush=True)
+        del b
+        L.swec_set_option(b"ctas_per_sm", 0)
     if args.reconstruct:
         S = shard & ~15
         d = [dat.data_ptr() + i * S for i in range(10)]

@@ -24,6 +24,11 @@ class SwecError(RuntimeError):
         super().__init__(f"{self.name}: {detail}" if detail else self.name)
 
 
+class ReconstructItem(C.Structure):
+    _fields_ = [("shards", C.POINTER(C.c_void_p)), ("present", C.POINTER(C.c_uint8)),
+                ("shard_len", C.c_size_t), ("data_only", C.c_int)]
+
+
 class Interval(C.Structure):
     _fields_ = [("block_index", C.c_int32), ("is_large_block", C.c_int32),
                 ("inner_block_offset", C.c_int64), ("size", C.c_int64),
@@ -47,9 +52,11 @@ PROTOTYPES = {
                                           C.POINTER(C.c_int), C.c_void_p]),
     "swec_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "swec_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "swec_reconstruct_batch": (C.c_int, [C.c_void_p, C.POINTER(ReconstructItem), C.c_int]),
     "swec_verify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "swec_encode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "swec_reconstruct_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "swec_apply_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "swec_encode_volume_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_void_p]),
     "swec_extract_data_shard_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
@@ -59,6 +66,8 @@ PROTOTYPES = {
     "swec_generate_ec_files": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "swec_rebuild_ec_files": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.POINTER(C.c_int)]),
+    "swec_verify_ec_files": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.POINTER(C.c_int)]),
     "swec_write_dat_file": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64]),
     "swec_expected_shard_size": (C.c_int64, [C.c_int64, C.c_int, C.c_int64, C.c_int64]),
     "swec_locate_data": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,

@@ -69,14 +69,21 @@ struct Slot {
 // K input streams + R computed streams per slot, pitch = chunk bytes.
 class FilePipeline {
   public:
-    FilePipeline(swec_encoder* enc, const Matrix& rows, size_t chunk) : enc_(enc), rows_(rows), chunk_(chunk) {}
+    // verify = true: streams [K, K+R) are the parity bytes read from disk; the computed parity goes to
+    // streams [K+R, K+2R) and is only compared on the device (no D2H, no writes).
+    FilePipeline(swec_encoder* enc, const Matrix& rows, size_t chunk, bool verify = false)
+        : enc_(enc), rows_(rows), chunk_(chunk), verify_(verify) {}
     ~FilePipeline() { shutdown(); }
 
     int start() {
         int rc = enc_->ensure_device();
         if (rc) return rc;
         const size_t nslots = env_sz("SWEC_STAGE_SLOTS", 3);
-        const size_t streams = size_t(rows_.cols + rows_.rows);
+        const size_t streams = size_t(rows_.cols + rows_.rows * (verify_ ? 2 : 1));
+        if (verify_) {
+            SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev_bad_), sizeof(unsigned long long) * size_t(rows_.rows)));
+            SWEC_CUDA(cudaMemset(dev_bad_, 0, sizeof(unsigned long long) * size_t(rows_.rows)));
+        }
         slots_.resize(nslots);
         for (auto& s : slots_) {
             s.host = static_cast<uint8_t*>(pinned_alloc(enc_->device, streams * chunk_));
@@ -122,21 +129,25 @@ class FilePipeline {
         const uint8_t* din[SWEC_MAX_SHARDS];
         uint8_t* dout[SWEC_MAX_SHARDS];
         for (int i = 0; i < K; i++) din[i] = s->dev + size_t(i) * chunk_;
-        if (len == chunk_) {  // full slot: the K input streams are contiguous — one DMA
-            e = cudaMemcpyAsync(s->dev, s->host, size_t(K) * chunk_, cudaMemcpyHostToDevice, s->stream);
+        const int nin = K + (verify_ ? R : 0);
+        if (len == chunk_) {  // full slot: the input streams are contiguous — one DMA
+            e = cudaMemcpyAsync(s->dev, s->host, size_t(nin) * chunk_, cudaMemcpyHostToDevice, s->stream);
         } else {
-            for (int i = 0; i < K && e == cudaSuccess; i++)
+            for (int i = 0; i < nin && e == cudaSuccess; i++)
                 e = cudaMemcpyAsync(s->dev + size_t(i) * chunk_, s->host + size_t(i) * chunk_, len, cudaMemcpyHostToDevice, s->stream);
         }
         if (e != cudaSuccess) return set_error(cuda_fail(e, "H2D"), s);
-        for (int r = 0; r < R; r++) dout[r] = s->dev + size_t(K + r) * chunk_;
+        for (int r = 0; r < R; r++) dout[r] = s->dev + size_t(K + (verify_ ? R : 0) + r) * chunk_;
         int rc;
         {
             std::lock_guard<std::mutex> lk(enc_->mu);
             rc = enc_->apply(rows_, din, dout, len, Layout{}, s->stream);
         }
         if (rc) return set_error(rc, s);
-        if (len == chunk_) {
+        if (verify_) {
+            for (int r = 0; r < R && e == cudaSuccess; r++)
+                e = launch_compare(dout[r], s->dev + size_t(K + r) * chunk_, len, dev_bad_ + r, s->stream);
+        } else if (len == chunk_) {
             e = cudaMemcpyAsync(s->host + size_t(K) * chunk_, dout[0], size_t(R) * chunk_, cudaMemcpyDeviceToHost, s->stream);
         } else {
             for (int r = 0; r < R && e == cudaSuccess; r++)
@@ -177,7 +188,16 @@ class FilePipeline {
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         slots_.clear();
+        if (dev_bad_) cudaFree(dev_bad_);
+        dev_bad_ = nullptr;
         started_ = false;
+    }
+
+    // verify mode, after finish(): mismatching 16-byte vectors per parity row
+    int mismatches(unsigned long long* out) {
+        if (!dev_bad_) return fail(SWEC_ERR_INVALID_ARG, "not a verify pipeline");
+        SWEC_CUDA(cudaMemcpy(out, dev_bad_, sizeof(unsigned long long) * size_t(rows_.rows), cudaMemcpyDeviceToHost));
+        return SWEC_OK;
     }
 
   private:
@@ -234,6 +254,8 @@ class FilePipeline {
     swec_encoder* enc_;
     Matrix rows_;
     size_t chunk_;
+    bool verify_ = false;
+    unsigned long long* dev_bad_ = nullptr;
     std::vector<Slot> slots_;
     std::deque<Slot*> free_, inflight_;
     std::mutex mu_;
@@ -465,6 +487,76 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
         return rc;
     }
     if (ragged) return fail(SWEC_ERR_SHARD_SIZE, "ec shard size expected 1048576 actual " + std::to_string(size % mib));
+    return SWEC_OK;
+}
+
+int swec_verify_ec_files(const char* base, const char* const* dirs, int ndirs, int k, int m, int device,
+                         uint64_t* mismatched_vectors, int* ok) {
+    if (!base || !ok || (ndirs > 0 && !dirs)) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    *ok = 0;
+    const std::string b(base);
+    if (k == 0) {
+        int ds = 0, ps = 0;
+        if (read_vif_ratio(b + ".vif", &ds, &ps) && ds > 0 && ps > 0 && ds + ps <= SWEC_MAX_SHARDS) { k = ds; m = ps; }
+        else { k = 10; m = 4; }
+    }
+    swec_encoder* enc = nullptr;
+    int rc = swec_encoder_new(k, m, device, &enc);
+    if (rc) return rc;
+    std::unique_ptr<swec_encoder, void (*)(swec_encoder*)> guard(enc, swec_encoder_free);
+    const int total = k + m;
+    std::string base_copy(b);
+    const std::string base_name = basename(&base_copy[0]);
+    FdSet fds;
+    std::vector<int> in(static_cast<size_t>(total), -1);
+    int64_t size = -1;
+    for (int i = 0; i < total; i++) {  // verify needs every shard (verify_ec_shards, ec_encoder.rs:177-278)
+        std::string path = b + shard_ext(i);
+        if (!file_exists(path)) {
+            path.clear();
+            for (int d = 0; d < ndirs; d++) {
+                const std::string cand = std::string(dirs[d]) + "/" + base_name + shard_ext(i);
+                if (file_exists(cand)) { path = cand; break; }
+            }
+        }
+        if (path.empty()) return fail(SWEC_ERR_TOO_FEW_SHARDS, "verify needs all shards; missing " + shard_ext(i));
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return io_fail("open " + path);
+        fds.fds.push_back(fd);
+        in[size_t(i)] = fd;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return io_fail("fstat shard");
+        if (size < 0) size = st.st_size;
+        else if (size != st.st_size)
+            return fail(SWEC_ERR_SHARD_SIZE, "ec shard size expected " + std::to_string(size) + " actual " + std::to_string(st.st_size));
+    }
+    Matrix rows(m, k);
+    memcpy(rows.v.data(), enc->gen.row(k), rows.v.size());
+    const size_t chunk = std::max<size_t>(256, (size_t(std::min<int64_t>(int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20)), std::max<int64_t>(size, 1))) + 255) & ~size_t(255));
+    FilePipeline pipe(enc, rows, chunk, /*verify=*/true);
+    if ((rc = pipe.start())) return rc;
+    for (int64_t o = 0; rc == SWEC_OK && o < size; o += int64_t(chunk)) {
+        Item it;
+        it.len = size_t(std::min<int64_t>(int64_t(chunk), size - o));
+        for (int i = 0; i < total; i++) it.reads.push_back({i, in[size_t(i)], o});
+        rc = pipe.submit(std::move(it));
+    }
+    const int rc2 = pipe.finish();
+    if (rc == SWEC_OK) rc = rc2;
+    std::vector<unsigned long long> bad(static_cast<size_t>(m), 0);
+    if (rc == SWEC_OK) rc = pipe.mismatches(bad.data());
+    const std::string msg = pipe.error_message();
+    pipe.shutdown();
+    if (rc) {
+        if (!msg.empty()) set_last_error(msg);
+        return rc;
+    }
+    bool all_ok = true;
+    for (int p = 0; p < m; p++) {
+        if (mismatched_vectors) mismatched_vectors[p] = bad[size_t(p)];
+        all_ok = all_ok && bad[size_t(p)] == 0;
+    }
+    *ok = all_ok ? 1 : 0;
     return SWEC_OK;
 }
 

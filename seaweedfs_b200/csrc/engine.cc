@@ -434,6 +434,79 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
     return rc;
 }
 
+// Many small intervals that share one matrix (degraded reads behind one dead server): pack them
+// back to back (each padded to 16 bytes) into slot-sized launches so the per-call costs — stream
+// round trip, launch, DMA set-up — are paid once per ~chunk instead of once per needle.
+struct Segment {
+    const uint8_t* const* in;  // K pointers
+    uint8_t* const* out;       // R pointers
+    size_t len;
+};
+
+static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std::vector<Segment>& segs) {
+    const int K = rows.cols, R = rows.rows;
+    if (R == 0 || segs.empty()) return SWEC_OK;
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    const size_t chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
+    if ((rc = e->ensure_slots(chunk))) return rc;
+    const size_t stride = e->slot_chunk;
+
+    struct Unpack { uint8_t* dst; const uint8_t* src; size_t len; };
+    std::vector<std::vector<Unpack>> pending(e->slots.size());
+    auto finish = [&](size_t si) -> int {
+        StagingSlot& sl = e->slots[si];
+        if (!sl.busy) return SWEC_OK;
+        SWEC_CUDA(cudaEventSynchronize(sl.done));
+        for (const Unpack& u : pending[si]) memcpy(u.dst, u.src, u.len);
+        pending[si].clear();
+        sl.busy = false;
+        return SWEC_OK;
+    };
+    size_t si = 0, fill = 0, nflush = 0;
+    auto flush = [&]() -> int {
+        if (fill == 0) return SWEC_OK;
+        StagingSlot& sl = e->slots[si];
+        const uint8_t* din[SWEC_MAX_INPUTS];
+        uint8_t* dout[SWEC_MAX_SHARDS];
+        for (int i = 0; i < K; i++) {
+            din[i] = sl.dev + size_t(i) * stride;
+            SWEC_CUDA(cudaMemcpyAsync(sl.dev + size_t(i) * stride, sl.host + size_t(i) * stride, fill,
+                                      cudaMemcpyHostToDevice, sl.stream));
+        }
+        for (int r = 0; r < R; r++) dout[r] = sl.dev + size_t(K + r) * stride;
+        const int rc2 = e->apply(rows, din, dout, fill, Layout{}, sl.stream);
+        if (rc2) return rc2;
+        for (int r = 0; r < R; r++)
+            SWEC_CUDA(cudaMemcpyAsync(sl.host + size_t(K + r) * stride, dout[r], fill, cudaMemcpyDeviceToHost, sl.stream));
+        SWEC_CUDA(cudaEventRecord(sl.done, sl.stream));
+        sl.busy = true;
+        fill = 0;
+        si = (++nflush) % e->slots.size();
+        return finish(si);  // the slot we are about to fill must be drained
+    };
+    for (const Segment& sg : segs) {
+        const size_t padded = (sg.len + 15) & ~size_t(15);
+        if (padded > stride) {  // larger than a slot: not a "small interval" — caller should not batch it
+            return fail(SWEC_ERR_INVALID_ARG, "batched interval larger than the staging chunk");
+        }
+        if (fill + padded > stride && (rc = flush())) return rc;
+        StagingSlot& sl = e->slots[si];
+        for (int i = 0; i < K; i++) {
+            uint8_t* dst = sl.host + size_t(i) * stride + fill;
+            memcpy(dst, sg.in[i], sg.len);
+            if (padded > sg.len) memset(dst + sg.len, 0, padded - sg.len);
+        }
+        for (int r = 0; r < R; r++) pending[si].push_back({sg.out[r], sl.host + size_t(K + r) * stride + fill, sg.len});
+        fill += padded;
+    }
+    if ((rc = flush())) return rc;
+    for (size_t i = 0; i < e->slots.size(); i++)
+        if ((rc = finish(i))) return rc;
+    return SWEC_OK;
+}
+
 }  // namespace swec
 
 // =================================================================== C ABI
@@ -571,6 +644,67 @@ int swec_reconstruct(swec_encoder* e, uint8_t* const* shards, const uint8_t* pre
     return apply_host(e, fused, ins, outs, n, nullptr);
 }
 
+int swec_reconstruct_batch(swec_encoder* e, const swec_reconstruct_item* items, int n_items) {
+    if (!e || (n_items > 0 && !items)) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    const int total = e->k + e->m;
+    const size_t chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
+    // group by (presence mask, data_only); big items take the ordinary streaming path
+    struct Group {
+        std::vector<int> ins, outs;
+        Matrix fused;
+        std::vector<Segment> segs;
+        std::vector<std::vector<const uint8_t*>> in_ptrs;
+        std::vector<std::vector<uint8_t*>> out_ptrs;
+    };
+    std::map<std::vector<uint8_t>, Group> groups;
+    for (int it = 0; it < n_items; it++) {
+        const swec_reconstruct_item& item = items[it];
+        if (!item.shards || !item.present) return fail(SWEC_ERR_INVALID_ARG, "NULL item field");
+        int npresent = 0;
+        for (int i = 0; i < total; i++) npresent += item.present[i] ? 1 : 0;
+        if (npresent == total) continue;
+        if (npresent < e->k) return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+        if (item.shard_len == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0 (ErrShardNoData)");
+        if (((item.shard_len + 15) & ~size_t(15)) > chunk) {
+            const int rc = swec_reconstruct(e, item.shards, item.present, item.shard_len, item.data_only);
+            if (rc) return rc;
+            continue;
+        }
+        std::vector<uint8_t> key(item.present, item.present + total);
+        for (auto& b : key) b = b ? 1 : 0;
+        key.push_back(item.data_only ? 1 : 0);
+        auto found = groups.find(key);
+        if (found == groups.end()) {
+            Group g;
+            if (!rs_reconstruct_plan(e->gen, e->k, key.data(), item.data_only != 0, &g.ins, &g.outs, &g.fused))
+                return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+            found = groups.emplace(key, std::move(g)).first;
+        }
+        Group& g = found->second;
+        if (g.outs.empty()) continue;
+        std::vector<const uint8_t*> ip;
+        std::vector<uint8_t*> op;
+        for (int idx : g.ins) ip.push_back(item.shards[idx]);
+        for (int idx : g.outs) {
+            if (!item.shards[idx]) return fail(SWEC_ERR_INVALID_ARG, "missing shard has no buffer");
+            op.push_back(item.shards[idx]);
+        }
+        g.in_ptrs.push_back(std::move(ip));
+        g.out_ptrs.push_back(std::move(op));
+        g.segs.push_back({nullptr, nullptr, item.shard_len});
+    }
+    for (auto& kv : groups) {
+        Group& g = kv.second;
+        for (size_t i = 0; i < g.segs.size(); i++) {  // pointer tables are stable now
+            g.segs[i].in = g.in_ptrs[i].data();
+            g.segs[i].out = g.out_ptrs[i].data();
+        }
+        const int rc = apply_host_packed(e, g.fused, g.segs);
+        if (rc) return rc;
+    }
+    return SWEC_OK;
+}
+
 int swec_verify(swec_encoder* e, uint8_t* const* shards, size_t n, int* ok) {
     if (!e || !shards || !ok) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
     if (n == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0");
@@ -610,6 +744,19 @@ int swec_reconstruct_device(swec_encoder* e, void* const* shards, const uint8_t*
     int rc = e->ensure_device();
     if (rc) return rc;
     return e->apply(fused, ins, outs, n, Layout{}, pick_stream(e, stream));
+}
+
+int swec_apply_device(swec_encoder* e, int r, int k, const uint8_t* rows, const void* const* in, void* const* out,
+                      size_t n, void* stream) {
+    if (!e || !rows || !in || !out || r <= 0 || k <= 0 || k > SWEC_MAX_INPUTS || r > SWEC_MAX_SHARDS)
+        return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    Matrix m(r, k);
+    memcpy(m.v.data(), rows, m.v.size());
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    return e->apply(m, reinterpret_cast<const uint8_t* const*>(in), reinterpret_cast<uint8_t* const*>(out), n,
+                    Layout{}, pick_stream(e, stream));
 }
 
 int64_t swec_expected_shard_size(int64_t dat_size, int k, int64_t large, int64_t small) {

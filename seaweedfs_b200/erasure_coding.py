@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._native import Interval, SwecError, check, lib
+from ._native import Interval, ReconstructItem, SwecError, check, lib
 
 DataShardsCount = 10                               # ec_encoder.go:20
 ParityShardsCount = 4                              # ec_encoder.go:21
@@ -115,6 +115,25 @@ class Encoder:
     def reconstruct_data(self, shards: list) -> None:
         self.reconstruct(shards, data_only=True)
 
+    def reconstruct_batch(self, batch: list[list], data_only: bool = True) -> None:
+        """Many Reconstruct/ReconstructData calls in one crossing (batched degraded reads): each
+        element is a shards list as for reconstruct(); missing entries are filled in place."""
+        items = (ReconstructItem * len(batch))()
+        keep = []
+        for j, shards in enumerate(batch):
+            n = self._check_shards(shards, allow_missing=True)
+            present = np.array([s is not None and len(s) > 0 for s in shards], dtype=np.uint8)
+            for i in range(self.total_shards):
+                if not present[i] and (i < self.data_shards or not data_only):
+                    shards[i] = np.zeros(n, dtype=np.uint8)
+            ptrs = _ptrs([s if s is not None and len(s) else None for s in shards])
+            keep.append((ptrs, present))
+            items[j].shards = C.cast(ptrs, C.POINTER(C.c_void_p))
+            items[j].present = present.ctypes.data_as(C.POINTER(C.c_uint8))
+            items[j].shard_len = n
+            items[j].data_only = int(data_only)
+        check(lib().swec_reconstruct_batch(self._h, items, len(batch)))
+
     def verify(self, shards: list[np.ndarray]) -> bool:
         n = self._check_shards(shards, allow_missing=False)
         ok = C.c_int(0)
@@ -129,6 +148,12 @@ class Encoder:
         pres = np.ascontiguousarray(np.asarray(present, dtype=np.uint8))
         check(lib().swec_reconstruct_device(self._h, _ptrs(shard_ptrs), pres.ctypes.data, shard_len,
                                             int(data_only), stream))
+
+    def apply_device(self, rows, in_ptrs, out_ptrs, shard_len: int, stream: int = 0) -> None:
+        """out[p] = XOR_i rows[p][i] ⊗ in[i] for an arbitrary matrix (device pointers)."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        check(lib().swec_apply_device(self._h, rows.shape[0], rows.shape[1], rows.ctypes.data, _ptrs(in_ptrs),
+                                      _ptrs(out_ptrs), shard_len, stream))
 
     def encode_volume_device(self, dat_ptr: int, dat_size: int, parity_ptrs, stream: int = 0,
                              large_block: int = ErasureCodingLargeBlockSize,
@@ -202,6 +227,19 @@ def rebuild_ec_files(base_file_name: str, additional_dirs: list[str] | None = No
     k, m, dev = (ctx.DataShards, ctx.ParityShards, ctx.device) if ctx else (0, 0, device)
     check(lib().swec_rebuild_ec_files(base_file_name.encode(), arr, len(dirs), k, m, dev, ids, C.byref(n)))
     return list(ids[: n.value])
+
+
+def verify_ec_files(base_file_name: str, additional_dirs: list[str] | None = None, ctx: ECContext | None = None,
+                    device: int = 0):
+    """Parity scrub of a shard set: returns (ok, mismatching 16-byte vectors per parity shard)."""
+    dirs = [d.encode() for d in (additional_dirs or [])]
+    arr = (C.c_char_p * max(1, len(dirs)))(*dirs) if dirs else None
+    k, m, dev = (ctx.DataShards, ctx.ParityShards, ctx.device) if ctx else (0, 0, device)
+    bad = (C.c_uint64 * MaxShardCount)()
+    ok = C.c_int(0)
+    check(lib().swec_verify_ec_files(base_file_name.encode(), arr, len(dirs), k, m, dev, bad, C.byref(ok)))
+    nm = ctx.ParityShards if ctx else ParityShardsCount
+    return bool(ok.value), list(bad[:nm])
 
 
 def write_dat_file(base_file_name: str, dat_file_size: int, shard_file_names: list[str],

@@ -202,6 +202,53 @@ def test_reconstruct_device_jit_and_tables_agree(cuda, swec, oracle):
         L.swec_set_option(b"jit_min_bytes", 64 << 20)
 
 
+@pytest.mark.parametrize("r,k", [(1, 1), (2, 3), (4, 10), (7, 12), (9, 5), (3, 32)])
+def test_apply_device_arbitrary_matrices(cuda, enc, r, k):
+    """The matrix-apply primitive on random r×k matrices (more than 4 / 8 rows span several launches)."""
+    from oracle import rs_numpy as rn
+    torch = cuda
+    rng = np.random.default_rng(r * 100 + k)
+    rows = rng.integers(0, 256, (r, k), dtype=np.uint8)
+    n = 50_000 + 7
+    ins = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(k)]
+    want = rn.apply_rows(rows, ins)
+    d = [dev(torch, x) for x in ins]
+    o = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(r)]
+    enc.apply_device(rows, [t.data_ptr() for t in d], [t.data_ptr() for t in o], n, stream(torch))
+    torch.cuda.synchronize()
+    for got, w in zip(o, want):
+        assert (got.cpu().numpy() == w).all()
+
+
+def test_reconstruct_batch_many_small_intervals(cuda, swec, enc, oracle):
+    """Batched degraded read: hundreds of needle-sized intervals, a few erasure patterns, ragged
+    lengths (1 B … 300 KB) — identical to per-call ReconstructData."""
+    rng = np.random.default_rng(99)
+    patterns = [(5,), (0, 11), (2, 3), (9,), (1, 4, 13)]
+    batch, truth = [], []
+    for j in range(240):
+        n = int(rng.choice([1, 7, 15, 16, 17, 100, 4096, 33_333, 300_000]))
+        data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+        full = data + oracle.encode(10, 4, data)
+        erased = patterns[j % len(patterns)]
+        batch.append([None if i in erased else s.copy() for i, s in enumerate(full)])
+        truth.append((full, erased))
+    launches0 = swec.lib().swec_kernel_launches()
+    enc.reconstruct_batch(batch, data_only=True)
+    launches = swec.lib().swec_kernel_launches() - launches0
+    for shards, (full, erased) in zip(batch, truth):
+        for i in erased:
+            if i < 10:
+                assert (shards[i] == full[i]).all()
+            else:
+                assert shards[i] is None
+    assert launches < 120, launches          # far fewer launches than the 240 calls it replaces
+    batch = [[None if i in e else s.copy() for i, s in enumerate(f)] for f, e in truth[:20]]
+    enc.reconstruct_batch(batch, data_only=False)
+    for shards, (full, erased) in zip(batch, truth[:20]):
+        assert all((shards[i] == full[i]).all() for i in range(14))
+
+
 def test_reconstruct_errors(cuda, enc):
     shards = [None] * 5 + [np.zeros(64, dtype=np.uint8) for _ in range(9)]
     with pytest.raises(Exception) as e:
@@ -332,6 +379,38 @@ def test_generate_and_rebuild_ec_files(cuda, swec, oracle, tmp_path):
         want[i].tofile(str(tmp_path / ("d.ec%02d" % i)))
     ec.write_dat_file(str(tmp_path / "d"), size, [str(tmp_path / ("d.ec%02d" % i)) for i in range(10)])
     assert (np.fromfile(str(tmp_path / "d.dat"), dtype=np.uint8) == dat).all()
+
+
+def test_verify_ec_files_scrub(cuda, swec, oracle, tmp_path):
+    """Parity scrub over files (Rust twin verify_ec_shards): clean set passes, a flipped byte in a
+    parity shard is pinned to that shard, a flipped data byte shows up in every parity shard."""
+    ec = swec.erasure_coding
+    size = 12_345_678
+    dat = oracle.synth(0, size, SEED + 3)
+    base = str(tmp_path / "21")
+    dat.tofile(base + ".dat")
+    ec.write_ec_files(base)
+    ok, bad = ec.verify_ec_files(base)
+    assert ok and bad == [0, 0, 0, 0]
+
+    def flip(path, off):
+        with open(path, "r+b") as f:
+            f.seek(off)
+            b = f.read(1)
+            f.seek(off)
+            f.write(bytes([b[0] ^ 0x40]))
+
+    flip(base + ".ec12", 777_777)
+    ok, bad = ec.verify_ec_files(base)
+    assert not ok and bad == [0, 0, 1, 0]
+    flip(base + ".ec12", 777_777)
+    flip(base + ".ec03", 5)
+    ok, bad = ec.verify_ec_files(base)
+    assert not ok and bad == [1, 1, 1, 1]
+    os.remove(base + ".ec07")
+    with pytest.raises(swec.SwecError) as e:
+        ec.verify_ec_files(base)
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS"
 
 
 def test_generate_ec_files_test_parameters_and_fixture(cuda, swec, oracle, kat, tmp_path):
