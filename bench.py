@@ -109,13 +109,18 @@ def _cpu_variants(seconds_each: float, threads: int):
     if po.gfni_level():
         kinds.append((1, "gfni_port_" + ("avx512" if po.gfni_level() == 2 else "avx2")))
     res, passes_used = {}, {}
+    # hyper-threads do not always help a memory-bound loop: try all logical CPUs and one per core
+    counts = sorted({threads, max(1, threads // 2)}, reverse=True)
     for kind, name in kinds:
-        probe = po.cpu_bench(kind, rows, per_shard, threads, 2)
-        if probe <= 0:
-            continue
-        passes = max(4, int(seconds_each * probe * 1e9 / (threads * 10 * per_shard)))
-        res[name] = round(po.cpu_bench(kind, rows, per_shard, threads, passes), 3)
-        passes_used[name] = passes
+        for tc in counts:
+            probe = po.cpu_bench(kind, rows, per_shard, tc, 2)
+            if probe <= 0:
+                continue
+            passes = max(4, int(seconds_each / len(counts) * probe * 1e9 / (tc * 10 * per_shard)))
+            got = round(po.cpu_bench(kind, rows, per_shard, tc, passes), 3)
+            if got > res.get(name, (0, 0))[0]:
+                res[name] = (got, tc)
+                passes_used[name] = passes
     if not res:
         raise RuntimeError("no CPU baseline available (oracle/_ref missing and no GFNI)")
     return res, passes_used, per_shard
@@ -124,12 +129,13 @@ def _cpu_variants(seconds_each: float, threads: int):
 def cpu_baseline(seconds_target: float = 12.0, threads: int | None = None):
     threads = threads or os.cpu_count() or 1
     res, passes, per_shard = _cpu_variants(seconds_target / 2, threads)
-    best = max(res, key=res.get)
-    return {"value": res[best], "unit": UNIT, "cores": threads,
+    best = max(res, key=lambda k: res[k][0])
+    return {"value": res[best][0], "unit": UNIT, "cores": res[best][1],
             "kind": "reference" if best.startswith("reference") else "port",
-            "sample": f"{threads} pinned threads x 10x{per_shard // MIB} MiB NUMA-local data shards, "
-                      f"{passes[best]} passes each (in-memory, no disk); best of {list(res)}",
-            "variants": res, "cpu_model": _cpu_model()}
+            "sample": f"{res[best][1]} pinned threads x 10x{per_shard // MIB} MiB NUMA-local data shards, "
+                      f"{passes[best]} passes each (in-memory, no disk); best of {list(res)} x thread counts",
+            "variants": {k: {"GBps": v[0], "threads": v[1]} for k, v in res.items()},
+            "logical_cpus": threads, "cpu_model": _cpu_model()}
 
 
 def _cpu_model():
@@ -163,12 +169,15 @@ def run_reference(args):
         return
     variants = {}
     for kind, label, name in kinds:
-        po.cpu_bench(kind, rows, per_shard, threads, max(1, args.warmup))      # untimed warm-up
-        variants[name] = (po.cpu_bench(kind, rows, per_shard, threads, args.steps * passes_per_step), label)
+        for tc in sorted({threads, max(1, threads // 2)}, reverse=True):
+            po.cpu_bench(kind, rows, per_shard, tc, max(1, args.warmup))      # untimed warm-up
+            got = po.cpu_bench(kind, rows, per_shard, tc, args.steps * passes_per_step)
+            if got > variants.get(name, (0, "", 0))[0]:
+                variants[name] = (got, label, tc)
     name = max(variants, key=lambda k: variants[k][0])
-    value, label = variants[name]
-    step_bytes = threads * passes_per_step * 10 * per_shard
-    sample = (f"{threads} pinned threads x {passes_per_step} passes over 10x{per_shard // MIB} MiB NUMA-local "
+    value, label, used = variants[name]
+    step_bytes = used * passes_per_step * 10 * per_shard
+    sample = (f"{used} pinned threads x {passes_per_step} passes over 10x{per_shard // MIB} MiB NUMA-local "
               f"data shards per step ({step_bytes / GIB:.1f} GiB of input per step), {name}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
@@ -176,8 +185,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "RS(10,4) encode, bounded in-memory sample of the 30 GiB volume workload",
                    "host": _cpu_model()},
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": label, "sample": sample,
-                         "variants": {k: round(v[0], 3) for k, v in variants.items()}},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": used, "kind": label, "sample": sample,
+                         "variants": {k: {"GBps": round(v[0], 3), "threads": v[2]} for k, v in variants.items()},
+                         "logical_cpus": threads},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

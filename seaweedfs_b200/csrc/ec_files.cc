@@ -21,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
+#include <memory>
 #include <thread>
 
 #include "engine.h"
@@ -66,6 +68,85 @@ struct Slot {
     Item item;
 };
 
+// A few I/O threads shared by the reader and the writer side: every shard file is independent, so
+// the k preads of a stripe (and the k+m pwrites of a finished one) run concurrently.  One thread
+// doing them serially tops out near 1.5 GB/s even on RAM-backed files.
+class IoPool {
+  public:
+    explicit IoPool(size_t n) {
+        for (size_t i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
+    }
+    ~IoPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // run fn(0..n-1) across the pool (the caller takes a share too); returns the first non-zero result
+    int parallel_for(int n, const std::function<int(int)>& fn) {
+        if (n <= 0) return 0;
+        Batch b;
+        b.fn = &fn;
+        b.n = n;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            batches_.push_back(&b);
+        }
+        cv_.notify_all();
+        work(&b);
+        std::unique_lock<std::mutex> lk(mu_);
+        b.done_cv.wait(lk, [&] { return b.finished == b.n; });
+        batches_.erase(std::find(batches_.begin(), batches_.end(), &b));
+        return b.rc;
+    }
+
+  private:
+    struct Batch {
+        const std::function<int(int)>* fn = nullptr;
+        int n = 0, next = 0, finished = 0, rc = 0;
+        std::condition_variable done_cv;
+    };
+    void work(Batch* b) {
+        for (;;) {
+            int i;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (b->next >= b->n) return;
+                i = b->next++;
+            }
+            const int rc = (*b->fn)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (rc && !b->rc) b->rc = rc;
+            if (++b->finished == b->n) b->done_cv.notify_all();
+        }
+    }
+    void loop() {
+        for (;;) {
+            Batch* b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] {
+                    if (stop_) return true;
+                    for (Batch* x : batches_)
+                        if (x->next < x->n) return true;
+                    return false;
+                });
+                if (stop_) return;
+                for (Batch* x : batches_)
+                    if (x->next < x->n) { b = x; break; }
+            }
+            if (b) work(b);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::deque<Batch*> batches_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
 // K input streams + R computed streams per slot, pitch = chunk bytes.
 class FilePipeline {
   public:
@@ -93,6 +174,7 @@ class FilePipeline {
             SWEC_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             free_.push_back(&s);
         }
+        io_.reset(new IoPool(env_sz("SWEC_IO_THREADS", std::min<size_t>(16, std::max<size_t>(4, std::thread::hardware_concurrency() / 4)))));
         writer_ = std::thread([this] { writer_loop(); });
         started_ = true;
         return SWEC_OK;
@@ -110,19 +192,27 @@ class FilePipeline {
         }
         const int K = rows_.cols, R = rows_.rows;
         const size_t len = item.len;
-        for (const ReadOp& r : item.reads) {
+        const std::function<int(int)> read_one = [&](int idx) -> int {
+            const ReadOp& r = item.reads[size_t(idx)];
             uint8_t* dst = s->host + size_t(r.stream) * chunk_;
             size_t got = 0;
             while (got < len) {
                 const ssize_t n = pread(r.fd, dst + got, len - got, off_t(r.off + int64_t(got)));
                 if (n < 0) {
                     if (errno == EINTR) continue;
-                    return set_error(io_fail("pread"), s);
+                    const int rc = io_fail("pread");
+                    note_error(last_error());
+                    return rc;
                 }
                 if (n == 0) break;  // EOF: the rest reads as zero (ec_encoder.go:258-262)
                 got += size_t(n);
             }
             if (got < len) memset(dst + got, 0, len - got);
+            return SWEC_OK;
+        };
+        if (const int rrc = io_->parallel_for(int(item.reads.size()), read_one)) {
+            set_last_error(noted_error());
+            return set_error(rrc, s);
         }
         if (cudaSetDevice(enc_->device) != cudaSuccess) return set_error(fail(SWEC_ERR_CUDA, "cudaSetDevice"), s);
         cudaError_t e = cudaSuccess;
@@ -179,6 +269,7 @@ class FilePipeline {
         }
         cv_.notify_all();
         if (writer_.joinable()) writer_.join();
+        io_.reset();
         cudaSetDevice(enc_->device);
         for (auto& s : slots_) {
             if (s.stream) cudaStreamSynchronize(s.stream);
@@ -201,6 +292,18 @@ class FilePipeline {
     }
 
   private:
+    // I/O runs on pool threads whose thread-local error text the submitting thread cannot see
+    void note_error(const char* msg) {
+        std::lock_guard<std::mutex> lk(note_mu_);
+        if (noted_.empty()) noted_ = msg;
+    }
+    std::string noted_error() {
+        std::lock_guard<std::mutex> lk(note_mu_);
+        return noted_;
+    }
+    std::mutex note_mu_;
+    std::string noted_;
+
     int set_error(int rc, Slot* s) {
         std::lock_guard<std::mutex> lk(mu_);
         if (!error_) {
@@ -224,19 +327,25 @@ class FilePipeline {
             }
             int rc = SWEC_OK;
             if (cudaEventSynchronize(s->done) != cudaSuccess) rc = fail(SWEC_ERR_CUDA, "cudaEventSynchronize failed in the shard writer");
-            for (const WriteOp& w : s->item.writes) {
-                if (rc) break;
-                const uint8_t* src = s->host + size_t(w.stream) * chunk_;
-                size_t put = 0;
-                while (put < s->item.len) {
-                    const ssize_t n = pwrite(w.fd, src + put, s->item.len - put, off_t(w.off + int64_t(put)));
-                    if (n < 0) {
-                        if (errno == EINTR) continue;
-                        rc = io_fail("pwrite");
-                        break;
+            if (!rc) {
+                const std::function<int(int)> write_one = [&](int idx) -> int {
+                    const WriteOp& w = s->item.writes[size_t(idx)];
+                    const uint8_t* src = s->host + size_t(w.stream) * chunk_;
+                    size_t put = 0;
+                    while (put < s->item.len) {
+                        const ssize_t n = pwrite(w.fd, src + put, s->item.len - put, off_t(w.off + int64_t(put)));
+                        if (n < 0) {
+                            if (errno == EINTR) continue;
+                            const int rc2 = io_fail("pwrite");
+                            note_error(last_error());
+                            return rc2;
+                        }
+                        put += size_t(n);
                     }
-                    put += size_t(n);
-                }
+                    return SWEC_OK;
+                };
+                rc = io_->parallel_for(int(s->item.writes.size()), write_one);
+                if (rc) set_last_error(noted_error());
             }
             {
                 std::lock_guard<std::mutex> lk(mu_);
@@ -261,6 +370,7 @@ class FilePipeline {
     std::mutex mu_;
     std::condition_variable cv_;
     std::thread writer_;
+    std::unique_ptr<IoPool> io_;
     int error_ = 0;
     std::string error_msg_;
     bool stop_ = false, started_ = false;

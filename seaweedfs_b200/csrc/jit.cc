@@ -14,6 +14,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -79,9 +80,18 @@ struct JitEntry {
     enum State { kCompiling, kReady, kFailed } state = kCompiling;
     std::shared_ptr<JitKernel> kernel;
 };
-std::mutex g_jit_mu;
-std::condition_variable g_jit_cv;
-std::map<std::vector<uint8_t>, JitEntry> g_jit_cache;  // process-wide
+// Process-wide cache.  Deliberately leaked (never destroyed): background compile threads may still be
+// finishing when static destructors run at process exit, and must find the map and mutex alive.
+std::mutex& g_jit_mu = *new std::mutex;
+std::condition_variable& g_jit_cv = *new std::condition_variable;
+std::map<std::vector<uint8_t>, JitEntry>& g_jit_cache = *new std::map<std::vector<uint8_t>, JitEntry>;
+int g_jit_inflight = 0;  // background compiles running (guarded by g_jit_mu)
+
+// at exit, give in-flight compiles a moment to land so no thread is inside NVRTC/cudart during teardown
+void jit_drain_at_exit() {
+    std::unique_lock<std::mutex> lock(g_jit_mu);
+    g_jit_cv.wait_for(lock, std::chrono::seconds(10), [] { return g_jit_inflight == 0; });
+}
 
 }  // namespace
 
@@ -177,14 +187,18 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
     }
     g_jit_cache[key].state = JitEntry::kCompiling;
     if (!wait) {
+        static const int registered = std::atexit(jit_drain_at_exit);
+        (void)registered;
         int dev = 0;
         cudaGetDevice(&dev);
+        g_jit_inflight++;
         std::thread([rows, key, threads, unroll, dev] {
             cudaSetDevice(dev);
             auto k = build_kernel(rows, threads, unroll);
             std::lock_guard<std::mutex> lk(g_jit_mu);
             g_jit_cache[key].kernel = k;
             g_jit_cache[key].state = k ? JitEntry::kReady : JitEntry::kFailed;
+            g_jit_inflight--;
             g_jit_cv.notify_all();
         }).detach();
         *out = nullptr;

@@ -318,6 +318,7 @@ def encode_volume_on_device(torch, enc, dat, large, small):
     (10 * (1 << 20), 1 << 30, 1 << 20),
     (10 * (1 << 20) + 1, 1 << 30, 1 << 20),
     (33_333_333, 1 << 30, 1 << 20),
+    (104_857_600, 1 << 30, 1 << 20),          # BASELINE configs[0]: 100 MiB volume, 10 small rows, shard 10 MiB
     (2_590_912, 10000, 100),                  # ec_test.go:19-30 block sizes (unaligned blocks)
     (10 * 4096 * 5 + 10 * 512 * 3 + 77, 4096, 512),   # large rows + small rows + ragged tail, aligned blocks
     (10 * 4096 * 3, 4096, 512),               # exact multiple of the large row (Issue 8947 shape)
