@@ -150,6 +150,20 @@ int swec_write_dat_file(const char *base_file_name, int64_t dat_file_size,
                         const char *const *shard_file_names, int data_shards,
                         int64_t large_block, int64_t small_block);
 
+/* ---- index files either side of the path (host only, no GPU) ---------------------------------- */
+/* WriteSortedFileFromIdx(base, ext): base.idx → base+ext (".ecx"), live entries sorted by needle id
+ * (ec_encoder.go:31-58).  Call it BEFORE writing shards, as VolumeEcShardsGenerate does.          */
+int swec_write_sorted_file_from_idx(const char *base_file_name, const char *ext);
+/* RebuildEcxFile: fold the .ecj deletion journal into .ecx, then remove .ecj
+ * (ec_volume_delete.go:95-142).                                                                  */
+int swec_rebuild_ecx_file(const char *base_file_name);
+/* WriteIdxFileFromEcIndex: .ecx (+ one tombstone per .ecj id) → .idx (ec_decoder.go:35-60).       */
+int swec_write_idx_file_from_ec_index(const char *base_file_name);
+/* HasLiveNeedles / FindDatFileSize (ec_decoder.go:23-33, 65-92).                                  */
+int swec_has_live_needles(const char *index_base_file_name, int *has_live);
+int swec_find_dat_file_size(const char *data_base_file_name, const char *index_base_file_name,
+                            int64_t *dat_size);
+
 /* ---- layout arithmetic (no GPU) ------------------------------------------------------------- */
 int64_t swec_expected_shard_size(int64_t dat_size, int data_shards, int64_t large_block,
                                  int64_t small_block);

@@ -232,3 +232,72 @@ def synth(byte_offset: int, n: int, seed: int) -> np.ndarray:
     b = z.astype("<u8").view(np.uint8)
     lo = byte_offset - first * 8
     return b[lo : lo + n].copy()
+
+
+# ---- index files either side of the path (no GF math) ------------------------------------------------
+# Entry = 8-byte id, 4-byte offset (units of 8 B), 4-byte size, big-endian
+# (weed/storage/types/needle_types.go:58-64, offset_4bytes.go:14-60).
+
+TOMBSTONE = -1
+
+
+def _entries(raw: bytes):
+    for off in range(0, len(raw) - len(raw) % 16, 16):
+        key = int.from_bytes(raw[off:off + 8], "big")
+        offset = int.from_bytes(raw[off + 8:off + 12], "big")
+        size = int.from_bytes(raw[off + 12:off + 16], "big", signed=True)
+        yield key, offset, size
+
+
+def _entry(key: int, offset: int, size: int) -> bytes:
+    return key.to_bytes(8, "big") + offset.to_bytes(4, "big") + (size & 0xFFFFFFFF).to_bytes(4, "big")
+
+
+def sorted_ecx_from_idx(idx: bytes) -> bytes:
+    """readNeedleMap + AscendingVisit (weed/storage/erasure_coding/ec_encoder.go:31-58,379-396)."""
+    live = {}
+    for key, offset, size in _entries(idx):
+        if offset != 0 and not (size < 0):
+            live[key] = (offset, size)
+        else:
+            live.pop(key, None)
+    return b"".join(_entry(k, *live[k]) for k in sorted(live))
+
+
+def fold_ecj_into_ecx(ecx: bytes, ecj: bytes) -> bytes:
+    """RebuildEcxFile (weed/storage/erasure_coding/ec_volume_delete.go:95-142): binary search, tombstone size."""
+    out = bytearray(ecx)
+    keys = [k for k, _, _ in _entries(ecx)]
+    for off in range(0, len(ecj) - len(ecj) % 8, 8):
+        nid = int.from_bytes(ecj[off:off + 8], "big")
+        lo, hi = 0, len(keys)
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if keys[mid] == nid:
+                out[mid * 16 + 12:mid * 16 + 16] = (TOMBSTONE & 0xFFFFFFFF).to_bytes(4, "big")
+                break
+            if keys[mid] < nid:
+                lo = mid + 1
+            else:
+                hi = mid
+    return bytes(out)
+
+
+def idx_from_ec_index(ecx: bytes, ecj: bytes) -> bytes:
+    """WriteIdxFileFromEcIndex (weed/storage/erasure_coding/ec_decoder.go:35-60)."""
+    out = bytearray(ecx)
+    for off in range(0, len(ecj) - len(ecj) % 8, 8):
+        out += _entry(int.from_bytes(ecj[off:off + 8], "big"), 0, TOMBSTONE)
+    return bytes(out)
+
+
+def find_dat_file_size(ecx: bytes, version: int) -> int:
+    """FindDatFileSize (ec_decoder.go:65-92) with GetActualSize (needle/needle_read.go:292-294,
+    needle_read_tail.go:36-50): header 16 + size + checksum 4 (+ timestamp 8 for v3) + padding 1..8."""
+    best = 8  # SuperBlockSize
+    for _key, offset, size in _entries(ecx):
+        if size < 0:
+            continue
+        fixed = 16 + size + 4 + (8 if version == 3 else 0)
+        best = max(best, offset * 8 + fixed + (8 - fixed % 8))
+    return best

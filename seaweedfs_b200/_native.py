@@ -69,6 +69,11 @@ PROTOTYPES = {
     "swec_verify_ec_files": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.POINTER(C.c_int)]),
     "swec_write_dat_file": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64]),
+    "swec_write_sorted_file_from_idx": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "swec_rebuild_ecx_file": (C.c_int, [C.c_char_p]),
+    "swec_write_idx_file_from_ec_index": (C.c_int, [C.c_char_p]),
+    "swec_has_live_needles": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
+    "swec_find_dat_file_size": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "swec_expected_shard_size": (C.c_int64, [C.c_int64, C.c_int, C.c_int64, C.c_int64]),
     "swec_locate_data": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                    C.POINTER(Interval), C.c_int]),

@@ -1,0 +1,215 @@
+// seaweedfs_b200/csrc/ec_index.cc — the index files either side of the RS path (SURVEY §8f row 4,
+// Appendix C).  No GF arithmetic here: host-only twins of
+//   WriteSortedFileFromIdx / readNeedleMap        weed/storage/erasure_coding/ec_encoder.go:31-58,379-396
+//   RebuildEcxFile / MarkNeedleDeleted            weed/storage/erasure_coding/ec_volume_delete.go:13-26,95-142
+//   SearchNeedleFromSortedIndex                   weed/storage/erasure_coding/ec_volume.go:431-458
+//   WriteIdxFileFromEcIndex, FindDatFileSize, HasLiveNeedles   weed/storage/erasure_coding/ec_decoder.go:23-92
+// so that a volume server using libswec for ec.encode / ec.rebuild / ec.decode needs nothing else
+// from the Go package for these files.  Entry format (4-byte offsets, the default build):
+// 8-byte needle id, 4-byte offset in units of 8 bytes, 4-byte size, all big-endian
+// (weed/storage/types/needle_types.go:58-64, offset_4bytes.go:14-60, needle_map/needle_value.go:24-30).
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace swec {
+namespace {
+
+constexpr int kEntry = 16;             // NeedleMapEntrySize
+constexpr int32_t kTombstone = -1;     // TombstoneFileSize
+constexpr int64_t kSuperBlockSize = 8; // super_block.SuperBlockSize
+
+uint64_t be64(const uint8_t* p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+    return v;
+}
+uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
+void put_be64(uint8_t* p, uint64_t v) {
+    for (int i = 7; i >= 0; i--) { p[i] = uint8_t(v); v >>= 8; }
+}
+void put_be32(uint8_t* p, uint32_t v) {
+    for (int i = 3; i >= 0; i--) { p[i] = uint8_t(v); v >>= 8; }
+}
+bool size_deleted(int32_t s) { return s < 0 || s == kTombstone; }  // Size.IsDeleted, needle_types.go:25-27
+
+bool read_all(const std::string& path, std::vector<uint8_t>* out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint8_t buf[1 << 16];
+    size_t n;
+    out->clear();
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->insert(out->end(), buf, buf + n);
+    fclose(f);
+    return true;
+}
+
+bool write_all(const std::string& path, const std::vector<uint8_t>& data) {
+    const int fd = open(path.c_str(), O_TRUNC | O_CREAT | O_WRONLY, 0644);
+    if (fd < 0) return false;
+    size_t put = 0;
+    while (put < data.size()) {
+        const ssize_t n = write(fd, data.data() + put, data.size() - put);
+        if (n < 0) {
+            if (errno == EINTR) continue;
+            close(fd);
+            return false;
+        }
+        put += size_t(n);
+    }
+    close(fd);
+    return true;
+}
+
+bool exists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+int io_err(const std::string& what) { return fail(SWEC_ERR_IO, what + ": " + strerror(errno)); }
+
+// GetActualSize (needle/needle_read.go:292-294, needle_read_tail.go:36-50): header 16 + body + checksum 4
+// (+ 8-byte timestamp in version 3) + padding to 8, where the padding is 1..8 bytes, never 0.
+int64_t actual_size(int32_t size, int version) {
+    const int64_t fixed = 16 + int64_t(size) + 4 + (version == 3 ? 8 : 0);
+    return fixed + (8 - fixed % 8);
+}
+
+}  // namespace
+}  // namespace swec
+
+using namespace swec;
+
+extern "C" {
+
+int swec_write_sorted_file_from_idx(const char* base, const char* ext) {
+    if (!base || !ext) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::vector<uint8_t> idx;
+    if (!read_all(std::string(base) + ".idx", &idx)) return io_err(std::string("cannot read Volume Index ") + base + ".idx");
+    // readNeedleMap: last live entry per key wins; a zero offset or deleted size removes the key
+    std::map<uint64_t, std::pair<uint32_t, uint32_t>> live;
+    for (size_t off = 0; off + kEntry <= idx.size(); off += kEntry) {
+        const uint64_t key = be64(&idx[off]);
+        const uint32_t offset = be32(&idx[off + 8]);
+        const uint32_t size = be32(&idx[off + 12]);
+        if (offset != 0 && !size_deleted(int32_t(size))) live[key] = {offset, size};
+        else live.erase(key);
+    }
+    std::vector<uint8_t> out(live.size() * kEntry);
+    size_t o = 0;
+    for (const auto& kv : live) {  // AscendingVisit
+        put_be64(&out[o], kv.first);
+        put_be32(&out[o + 8], kv.second.first);
+        put_be32(&out[o + 12], kv.second.second);
+        o += kEntry;
+    }
+    if (!write_all(std::string(base) + ext, out)) return io_err("failed to open ecx file");
+    return SWEC_OK;
+}
+
+int swec_rebuild_ecx_file(const char* base) {
+    if (!base) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    const std::string b(base);
+    if (!exists(b + ".ecj")) return SWEC_OK;
+    const int ecx = open((b + ".ecx").c_str(), O_RDWR);
+    if (ecx < 0) return io_err("rebuild: failed to open ecx file");
+    struct stat st;
+    fstat(ecx, &st);
+    const int64_t entries = st.st_size / kEntry;
+    std::vector<uint8_t> ecj;
+    if (!read_all(b + ".ecj", &ecj)) {
+        close(ecx);
+        return io_err("rebuild: failed to open ecj file");
+    }
+    for (size_t off = 0; off + 8 <= ecj.size(); off += 8) {
+        const uint64_t id = be64(&ecj[off]);
+        int64_t lo = 0, hi = entries;  // SearchNeedleFromSortedIndex
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            uint8_t e[kEntry];
+            if (pread(ecx, e, kEntry, off_t(mid * kEntry)) != kEntry) {
+                close(ecx);
+                return io_err("ecx read");
+            }
+            const uint64_t key = be64(e);
+            if (key == id) {  // MarkNeedleDeleted: tombstone the size field in place
+                uint8_t t[4];
+                put_be32(t, uint32_t(kTombstone));
+                if (pwrite(ecx, t, 4, off_t(mid * kEntry + 12)) != 4) {
+                    close(ecx);
+                    return io_err("sorted needle write error");
+                }
+                break;
+            }
+            if (key < id) lo = mid + 1;
+            else hi = mid;
+        }
+    }
+    close(ecx);
+    unlink((b + ".ecj").c_str());
+    return SWEC_OK;
+}
+
+int swec_write_idx_file_from_ec_index(const char* base) {
+    if (!base) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    const std::string b(base);
+    std::vector<uint8_t> data;
+    if (!read_all(b + ".ecx", &data)) return io_err("cannot open ec index " + b + ".ecx");
+    std::vector<uint8_t> ecj;
+    if (exists(b + ".ecj") && !read_all(b + ".ecj", &ecj)) return io_err("cannot open ec index " + b + ".ecj");
+    for (size_t off = 0; off + 8 <= ecj.size(); off += 8) {  // one tombstone entry per journalled id
+        uint8_t e[kEntry] = {0};
+        memcpy(e, &ecj[off], 8);
+        put_be32(e + 12, uint32_t(kTombstone));
+        data.insert(data.end(), e, e + kEntry);
+    }
+    if (!write_all(b + ".idx", data)) return io_err("cannot open " + b + ".idx");
+    return SWEC_OK;
+}
+
+int swec_has_live_needles(const char* index_base, int* has_live) {
+    if (!index_base || !has_live) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::vector<uint8_t> ecx;
+    if (!read_all(std::string(index_base) + ".ecx", &ecx)) return io_err(std::string("cannot open ec index ") + index_base + ".ecx");
+    *has_live = 0;
+    for (size_t off = 0; off + kEntry <= ecx.size(); off += kEntry)
+        if (!size_deleted(int32_t(be32(&ecx[off + 12])))) {
+            *has_live = 1;
+            break;
+        }
+    return SWEC_OK;
+}
+
+int swec_find_dat_file_size(const char* data_base, const char* index_base, int64_t* dat_size) {
+    if (!data_base || !index_base || !dat_size) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    // readEcVolumeVersion: the superblock sits at the start of .ec00; byte 0 is the needle version
+    const int fd = open((std::string(data_base) + ".ec00").c_str(), O_RDONLY);
+    if (fd < 0) return io_err(std::string("open ec volume ") + data_base + " superblock");
+    uint8_t sb[kSuperBlockSize];
+    const ssize_t got = pread(fd, sb, sizeof sb, 0);
+    close(fd);
+    if (got != ssize_t(sizeof sb)) return fail(SWEC_ERR_IO, "cannot read the superblock from .ec00");
+    const int version = sb[0];
+    std::vector<uint8_t> ecx;
+    if (!read_all(std::string(index_base) + ".ecx", &ecx)) return io_err(std::string("cannot open ec index ") + index_base + ".ecx");
+    int64_t size = kSuperBlockSize;
+    for (size_t off = 0; off + kEntry <= ecx.size(); off += kEntry) {
+        const int32_t sz = int32_t(be32(&ecx[off + 12]));
+        if (size_deleted(sz)) continue;
+        const int64_t stop = int64_t(be32(&ecx[off + 8])) * 8 + actual_size(sz, version);
+        if (stop > size) size = stop;
+    }
+    *dat_size = size;
+    return SWEC_OK;
+}
+
+}  // extern "C"

@@ -249,6 +249,38 @@ def write_dat_file(base_file_name: str, dat_file_size: int, shard_file_names: li
     check(lib().swec_write_dat_file(base_file_name.encode(), dat_file_size, names, data_shards, large_block, small_block))
 
 
+# ---- index files (.idx / .ecx / .ecj) --------------------------------------------------------------
+
+def write_sorted_file_from_idx(base_file_name: str, ext: str = ".ecx") -> None:
+    """WriteSortedFileFromIdx (ec_encoder.go:31-58)"""
+    check(lib().swec_write_sorted_file_from_idx(base_file_name.encode(), ext.encode()))
+
+
+def rebuild_ecx_file(base_file_name: str) -> None:
+    """RebuildEcxFile (ec_volume_delete.go:95-142)"""
+    check(lib().swec_rebuild_ecx_file(base_file_name.encode()))
+
+
+def write_idx_file_from_ec_index(base_file_name: str) -> None:
+    """WriteIdxFileFromEcIndex (ec_decoder.go:35-60)"""
+    check(lib().swec_write_idx_file_from_ec_index(base_file_name.encode()))
+
+
+def has_live_needles(index_base_file_name: str) -> bool:
+    v = C.c_int(0)
+    check(lib().swec_has_live_needles(index_base_file_name.encode(), C.byref(v)))
+    return bool(v.value)
+
+
+def find_dat_file_size(data_base_file_name: str, index_base_file_name: str) -> int:
+    v = C.c_int64(0)
+    check(lib().swec_find_dat_file_size(data_base_file_name.encode(), index_base_file_name.encode(), C.byref(v)))
+    return int(v.value)
+
+
+WriteSortedFileFromIdx, RebuildEcxFile, WriteIdxFileFromEcIndex = (write_sorted_file_from_idx, rebuild_ecx_file,
+                                                                    write_idx_file_from_ec_index)
+HasLiveNeedles, FindDatFileSize = has_live_needles, find_dat_file_size
 WriteEcFiles, WriteEcFilesWithContext = write_ec_files, write_ec_files
 generateEcFiles, RebuildEcFiles, WriteDatFile = generate_ec_files, rebuild_ec_files, write_dat_file
 
