@@ -142,6 +142,10 @@ int swec_encoder_impl::ensure_device() {
 int swec_encoder_impl::ensure_slots(size_t chunk) {
     const size_t nslots = size_t(std::max(2l, g_opt_stage_slots.load()));
     if (!slots.empty() && slot_chunk >= chunk && slots.size() == nslots) return SWEC_OK;
+    // grow geometrically (callers with varying sizes must not re-pin memory on every larger call)
+    if (!slots.empty() && slot_chunk < chunk)
+        chunk = std::min(std::max(chunk, 2 * slot_chunk), std::max(chunk, size_t(g_opt_stage_chunk.load())));
+    chunk = std::max<size_t>(chunk, 64 * 1024);
     for (auto& s : slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.host) pinned_free(s.host);
@@ -381,43 +385,58 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
         return SWEC_OK;
     };
 
+    bool all_in_bounced = true, all_out_bounced = !check;
+    for (int i = 0; i < K; i++) all_in_bounced = all_in_bounced && !in_direct[size_t(i)];
+    for (int r = 0; r < R; r++) all_out_bounced = all_out_bounced && !out_direct[size_t(r)];
+
     size_t ci = 0;
     for (size_t off = 0; off < n; off += chunk, ci++) {
         const size_t si = ci % e->slots.size();
         StagingSlot& s = e->slots[si];
         if ((rc = finish(si))) break;
         const size_t len = std::min(chunk, n - off);
+        // Pageable callers (Go heap memory) bounce through the slot anyway, so pack the streams at a
+        // pitch that fits this call: one DMA in, one DMA out instead of k + m small ones.
+        const size_t pitch = all_in_bounced && all_out_bounced ? ((len + 255) & ~size_t(255)) : stride;
         const uint8_t* din[SWEC_MAX_INPUTS];
         uint8_t* dout[SWEC_MAX_SHARDS];
         for (int i = 0; i < K; i++) {
-            uint8_t* d = s.dev + size_t(i) * stride;
+            uint8_t* d = s.dev + size_t(i) * pitch;
             din[i] = d;
             const uint8_t* src = in[i] + off;
             if (!in_direct[size_t(i)]) {
-                memcpy(s.host + size_t(i) * stride, src, len);
-                src = s.host + size_t(i) * stride;
+                memcpy(s.host + size_t(i) * pitch, src, len);
+                src = s.host + size_t(i) * pitch;
             }
-            SWEC_CUDA(cudaMemcpyAsync(d, src, len, cudaMemcpyDefault, s.stream));
+            if (pitch == stride) SWEC_CUDA(cudaMemcpyAsync(d, src, len, cudaMemcpyDefault, s.stream));
         }
-        for (int r = 0; r < R; r++) dout[r] = s.dev + size_t(K + r) * stride;
+        if (pitch != stride)
+            SWEC_CUDA(cudaMemcpyAsync(s.dev, s.host, size_t(K - 1) * pitch + len, cudaMemcpyHostToDevice, s.stream));
+        for (int r = 0; r < R; r++) dout[r] = s.dev + size_t(K + r) * pitch;
         if ((rc = e->apply(rows, din, dout, len, Layout{}, s.stream))) break;
-        for (int r = 0; r < R; r++) {
-            if (check) {
-                // bring the caller's copy of this row next to the computed one and compare in HBM
-                uint8_t* theirs = s.dev + size_t(K + R + r) * stride;
-                const uint8_t* src = out[r] + off;
-                if (!out_direct[size_t(r)]) {
-                    memcpy(s.host + size_t(K + r) * stride, src, len);
-                    src = s.host + size_t(K + r) * stride;
+        if (pitch != stride) {
+            SWEC_CUDA(cudaMemcpyAsync(s.host + size_t(K) * pitch, dout[0], size_t(R - 1) * pitch + len,
+                                      cudaMemcpyDeviceToHost, s.stream));
+            for (int r = 0; r < R; r++) pending[si].push_back({out[r] + off, s.host + size_t(K + r) * pitch, len});
+        } else {
+            for (int r = 0; r < R; r++) {
+                if (check) {
+                    // bring the caller's copy of this row next to the computed one and compare in HBM
+                    uint8_t* theirs = s.dev + size_t(K + R + r) * stride;
+                    const uint8_t* src = out[r] + off;
+                    if (!out_direct[size_t(r)]) {
+                        memcpy(s.host + size_t(K + r) * stride, src, len);
+                        src = s.host + size_t(K + r) * stride;
+                    }
+                    SWEC_CUDA(cudaMemcpyAsync(theirs, src, len, cudaMemcpyDefault, s.stream));
+                    SWEC_CUDA(launch_compare(dout[r], theirs, len, dev_bad, s.stream));
+                } else if (out_direct[size_t(r)]) {
+                    SWEC_CUDA(cudaMemcpyAsync(out[r] + off, dout[r], len, cudaMemcpyDefault, s.stream));
+                } else {
+                    uint8_t* bounce = s.host + size_t(K + r) * stride;
+                    SWEC_CUDA(cudaMemcpyAsync(bounce, dout[r], len, cudaMemcpyDeviceToHost, s.stream));
+                    pending[si].push_back({out[r] + off, bounce, len});
                 }
-                SWEC_CUDA(cudaMemcpyAsync(theirs, src, len, cudaMemcpyDefault, s.stream));
-                SWEC_CUDA(launch_compare(dout[r], theirs, len, dev_bad, s.stream));
-            } else if (out_direct[size_t(r)]) {
-                SWEC_CUDA(cudaMemcpyAsync(out[r] + off, dout[r], len, cudaMemcpyDefault, s.stream));
-            } else {
-                uint8_t* bounce = s.host + size_t(K + r) * stride;
-                SWEC_CUDA(cudaMemcpyAsync(bounce, dout[r], len, cudaMemcpyDeviceToHost, s.stream));
-                pending[si].push_back({out[r] + off, bounce, len});
             }
         }
         SWEC_CUDA(cudaEventRecord(s.done, s.stream));
