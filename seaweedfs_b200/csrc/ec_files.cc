@@ -87,16 +87,13 @@ class IoPool {
     // run fn(0..n-1) across the pool (the caller takes a share too); returns the first non-zero result
     int parallel_for(int n, const std::function<int(int)>& fn) {
         if (n <= 0) return 0;
-        Batch b;
+        Batch b;  // lives on this stack frame: nobody may touch it once finished == n has been observed
         b.fn = &fn;
         b.n = n;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            batches_.push_back(&b);
-        }
-        cv_.notify_all();
-        work(&b);
         std::unique_lock<std::mutex> lk(mu_);
+        batches_.push_back(&b);
+        cv_.notify_all();
+        work(&b, lk);
         b.done_cv.wait(lk, [&] { return b.finished == b.n; });
         batches_.erase(std::find(batches_.begin(), batches_.end(), &b));
         return b.rc;
@@ -108,36 +105,34 @@ class IoPool {
         int n = 0, next = 0, finished = 0, rc = 0;
         std::condition_variable done_cv;
     };
-    void work(Batch* b) {
-        for (;;) {
-            int i;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (b->next >= b->n) return;
-                i = b->next++;
-            }
-            const int rc = (*b->fn)(i);
-            std::lock_guard<std::mutex> lk(mu_);
+    // Called and returns with mu_ held.  A batch is only dereferenced while the lock has been held
+    // continuously since we last saw it unfinished (its owner cannot return without the lock).
+    void work(Batch* b, std::unique_lock<std::mutex>& lk) {
+        while (b->next < b->n) {
+            const int i = b->next++;
+            const std::function<int(int)>* fn = b->fn;
+            lk.unlock();
+            const int rc = (*fn)(i);
+            lk.lock();
             if (rc && !b->rc) b->rc = rc;
-            if (++b->finished == b->n) b->done_cv.notify_all();
+            if (++b->finished == b->n) {
+                b->done_cv.notify_all();
+                return;  // the owner may destroy the batch as soon as we release the lock
+            }
         }
     }
     void loop() {
+        std::unique_lock<std::mutex> lk(mu_);
         for (;;) {
             Batch* b = nullptr;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] {
-                    if (stop_) return true;
-                    for (Batch* x : batches_)
-                        if (x->next < x->n) return true;
-                    return false;
-                });
-                if (stop_) return;
+            cv_.wait(lk, [&] {
+                if (stop_) return true;
                 for (Batch* x : batches_)
-                    if (x->next < x->n) { b = x; break; }
-            }
-            if (b) work(b);
+                    if (x->next < x->n) { b = x; return true; }
+                return false;
+            });
+            if (stop_) return;
+            if (b) work(b, lk);
         }
     }
     std::vector<std::thread> threads_;
