@@ -16,6 +16,7 @@
 #include <cstring>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -77,20 +78,63 @@ Nvrtc& nvrtc() {
 }
 
 struct JitEntry {
-    enum State { kCompiling, kReady, kFailed } state = kCompiling;
+    enum State { kCold, kQueued, kCompiling, kReady, kFailed } state = kCold;
+    int uses = 0;  // short-stream requests seen while cold
     std::shared_ptr<JitKernel> kernel;
 };
-// Process-wide cache.  Deliberately leaked (never destroyed): background compile threads may still be
-// finishing when static destructors run at process exit, and must find the map and mutex alive.
-std::mutex& g_jit_mu = *new std::mutex;
-std::condition_variable& g_jit_cv = *new std::condition_variable;
-std::map<std::vector<uint8_t>, JitEntry>& g_jit_cache = *new std::map<std::vector<uint8_t>, JitEntry>;
-int g_jit_inflight = 0;  // background compiles running (guarded by g_jit_mu)
+struct JitRequest {
+    Matrix rows;
+    std::vector<uint8_t> key;
+    int threads, unroll, device;
+};
+// Process-wide state.  Deliberately leaked (never destroyed): the compiler thread may still be
+// finishing when static destructors run at process exit and must find the map and mutex alive.
+struct JitGlobal {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::map<std::vector<uint8_t>, JitEntry> cache;
+    std::deque<JitRequest> queue;  // background compiles, served by ONE worker thread
+    std::thread worker;
+    bool worker_started = false, stop = false;
+};
+JitGlobal& G() {
+    static JitGlobal* g = new JitGlobal;
+    return *g;
+}
+constexpr int kHotUses = 2;        // a matrix is worth a background compile from its 2nd short use
+constexpr size_t kMaxQueued = 16;  // beyond that the table kernel keeps serving
 
-// at exit, give in-flight compiles a moment to land so no thread is inside NVRTC/cudart during teardown
-void jit_drain_at_exit() {
-    std::unique_lock<std::mutex> lock(g_jit_mu);
-    g_jit_cv.wait_for(lock, std::chrono::seconds(10), [] { return g_jit_inflight == 0; });
+std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll);
+
+void jit_worker_loop() {
+    JitGlobal& g = G();
+    std::unique_lock<std::mutex> lock(g.mu);
+    for (;;) {
+        g.cv.wait(lock, [&] { return g.stop || !g.queue.empty(); });
+        if (g.stop) return;
+        JitRequest rq = std::move(g.queue.front());
+        g.queue.pop_front();
+        g.cache[rq.key].state = JitEntry::kCompiling;
+        lock.unlock();
+        cudaSetDevice(rq.device);
+        auto k = build_kernel(rq.rows, rq.threads, rq.unroll);
+        lock.lock();
+        g.cache[rq.key].kernel = k;
+        g.cache[rq.key].state = k ? JitEntry::kReady : JitEntry::kFailed;
+        g.cv.notify_all();
+    }
+}
+
+// at exit: let the compile in progress (≤ ~1 s) land, then stop the worker before NVRTC/cudart go away
+void jit_stop_at_exit() {
+    JitGlobal& g = G();
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        g.stop = true;
+        g.queue.clear();
+    }
+    g.cv.notify_all();
+    if (g.worker.joinable()) g.worker.join();
 }
 
 }  // namespace
@@ -141,7 +185,8 @@ static int compile_cubin(const Matrix& rows, int threads, int unroll, std::vecto
     return SWEC_OK;
 }
 
-static std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll) {
+namespace {
+std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll) {
     auto kernel = std::make_shared<JitKernel>();
     kernel->threads = threads;
     kernel->unroll = unroll;
@@ -157,62 +202,68 @@ static std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, 
     return kernel;
 }
 
-// Cache entry states: absent → (compiling) → ready | failed.  wait = true compiles inline (long
-// streams: the ≈0.3 s is amortised); wait = false starts a background compile and reports "not
-// ready" so the caller serves this call from the table kernel and later calls from the fast one.
+}  // namespace
+
+// Long streams (wait = true) compile inline on the calling thread — ≈0.3 s, amortised.  Short ones never
+// block: they are served by the table kernel, and a matrix that keeps coming back (degraded reads
+// behind one dead server) is compiled once by the background worker and picked up when ready.
 int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait) {
     const int threads = int(g_opt_enc_threads.load()), unroll = int(g_opt_enc_unroll.load());
     const std::vector<uint8_t> key = jit_key(rows, threads, unroll);
+    *out = nullptr;
     auto local = enc->jit.find(key);
     if (local != enc->jit.end()) {
         *out = local->second;
         return SWEC_OK;
     }
     if (!nvrtc().ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
-    std::unique_lock<std::mutex> lock(g_jit_mu);
+    JitGlobal& g = G();
+    std::unique_lock<std::mutex> lock(g.mu);
     for (;;) {
-        auto it = g_jit_cache.find(key);
-        if (it == g_jit_cache.end()) break;
-        if (it->second.state == JitEntry::kCompiling) {
-            if (!wait) {
-                *out = nullptr;
-                return SWEC_OK;
+        JitEntry& e = g.cache[key];
+        if (e.state == JitEntry::kReady || e.state == JitEntry::kFailed) {
+            enc->jit[key] = e.kernel;  // remember either outcome
+            *out = e.kernel;
+            return e.kernel ? SWEC_OK : SWEC_ERR_JIT;
+        }
+        if (!wait) {
+            if (e.state == JitEntry::kCold && ++e.uses >= kHotUses && g.queue.size() < kMaxQueued && !g.stop) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                e.state = JitEntry::kQueued;
+                g.queue.push_back({rows, key, threads, unroll, dev});
+                if (!g.worker_started) {
+                    g.worker_started = true;
+                    g.worker = std::thread(jit_worker_loop);
+                    std::atexit(jit_stop_at_exit);
+                }
+                g.cv.notify_all();
             }
-            g_jit_cv.wait(lock);
+            return SWEC_OK;  // not ready: *out stays null
+        }
+        if (e.state == JitEntry::kCompiling) {  // someone else is on it
+            g.cv.wait(lock);
             continue;
         }
-        enc->jit[key] = it->second.kernel;  // ready or failed (nullptr): remember either way
-        *out = it->second.kernel;
-        return it->second.kernel ? SWEC_OK : SWEC_ERR_JIT;
+        if (e.state == JitEntry::kQueued) {  // take it over from the queue
+            for (auto it = g.queue.begin(); it != g.queue.end(); ++it)
+                if (it->key == key) {
+                    g.queue.erase(it);
+                    break;
+                }
+        }
+        e.state = JitEntry::kCompiling;
+        lock.unlock();
+        auto k = build_kernel(rows, threads, unroll);
+        lock.lock();
+        JitEntry& e2 = g.cache[key];
+        e2.kernel = k;
+        e2.state = k ? JitEntry::kReady : JitEntry::kFailed;
+        g.cv.notify_all();
+        enc->jit[key] = k;
+        *out = k;
+        return k ? SWEC_OK : SWEC_ERR_JIT;
     }
-    g_jit_cache[key].state = JitEntry::kCompiling;
-    if (!wait) {
-        static const int registered = std::atexit(jit_drain_at_exit);
-        (void)registered;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        g_jit_inflight++;
-        std::thread([rows, key, threads, unroll, dev] {
-            cudaSetDevice(dev);
-            auto k = build_kernel(rows, threads, unroll);
-            std::lock_guard<std::mutex> lk(g_jit_mu);
-            g_jit_cache[key].kernel = k;
-            g_jit_cache[key].state = k ? JitEntry::kReady : JitEntry::kFailed;
-            g_jit_inflight--;
-            g_jit_cv.notify_all();
-        }).detach();
-        *out = nullptr;
-        return SWEC_OK;
-    }
-    lock.unlock();
-    auto k = build_kernel(rows, threads, unroll);
-    lock.lock();
-    g_jit_cache[key].kernel = k;
-    g_jit_cache[key].state = k ? JitEntry::kReady : JitEntry::kFailed;
-    g_jit_cv.notify_all();
-    enc->jit[key] = k;
-    *out = k;
-    return k ? SWEC_OK : SWEC_ERR_JIT;
 }
 
 int jit_debug_compile(const Matrix& rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
