@@ -60,6 +60,10 @@ const char *swec_version(void);
 const char *swec_strerror(int status);
 const char *swec_last_error(void);            /* thread-local detail of the last failure        */
 int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the driver is absent   */
+/* Stop the library's background compiler thread (idempotent).  Embedders whose runtime tears the
+ * process down in stages (CPython's Py_Finalize) call this from their own exit hook; the library
+ * also registers it with atexit().  Everything keeps working afterwards, without background JIT. */
+void swec_shutdown(void);
 uint64_t swec_kernel_launches(void);          /* kernels this process has launched (all devices) */
 /* Tuning: "enc_threads" {128,256,512}, "enc_unroll" {1,2}, "ctas_per_sm" (0 = auto),
  * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "jit" {0,1},

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "swec_strerror": (C.c_char_p, [C.c_int]),
     "swec_last_error": (C.c_char_p, []),
     "swec_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "swec_shutdown": (None, []),
     "swec_kernel_launches": (C.c_uint64, []),
     "swec_set_option": (C.c_int, [C.c_char_p, C.c_long]),
     "swec_debug_jit_compile": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_int),
@@ -105,6 +106,8 @@ def lib() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        import atexit
+        atexit.register(L.swec_shutdown)   # before the interpreter starts tearing modules down
     return _lib
 
 

@@ -6,11 +6,40 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <execinfo.h>
+#include <signal.h>
 #include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 
 namespace swec {
+
+// ------------------------------------------------------------------ crash diagnostics (SWEC_DEBUG_SEGV=1)
+static void segv_backtrace(int sig) {
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "\n[swec] fatal signal, backtrace:\n";
+    if (write(2, msg, sizeof msg - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+static const int g_segv_hook = [] {
+    if (getenv("SWEC_DEBUG_SEGV")) {
+        signal(SIGSEGV, segv_backtrace);
+        signal(SIGABRT, segv_backtrace);
+        signal(SIGBUS, segv_backtrace);
+        // Python's faulthandler restores the default handlers when the interpreter finalises; hook
+        // again once exit() starts running handlers so crashes in static destructors are seen too
+        std::atexit([] {
+            signal(SIGSEGV, segv_backtrace);
+            signal(SIGABRT, segv_backtrace);
+            const char m[] = "[swec] exit handlers running\n";
+            if (write(2, m, sizeof m - 1) < 0) {}
+        });
+    }
+    return 0;
+}();
 
 // ------------------------------------------------------------------ errors
 
@@ -565,6 +594,8 @@ int swec_device_count(int* count) {
 }
 
 uint64_t swec_kernel_launches(void) { return g_kernel_launches.load(); }
+
+void swec_shutdown(void) { jit_shutdown(); }
 
 int swec_debug_jit_compile(int r, int k, const uint8_t* rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
     if (r <= 0 || k <= 0 || k > SWEC_MAX_INPUTS || !rows) return fail(SWEC_ERR_INVALID_ARG, "bad matrix");

@@ -86,6 +86,7 @@ bool jit_available();
 // Specialised Horner kernel for `rows` on the current device (compiled once per matrix/process).
 int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait = true);
 int jit_debug_compile(const Matrix& rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops);
+void jit_shutdown();  // stop the background compiler (idempotent); inline compiles keep working
 bool jit_cached(swec_encoder_impl* enc, const Matrix& rows);
 cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocked, cudaStream_t s);
 

@@ -141,6 +141,8 @@ void jit_stop_at_exit() {
 
 bool jit_available() { return nvrtc().ok; }
 
+void jit_shutdown() { jit_stop_at_exit(); }
+
 static std::vector<uint8_t> jit_key(const Matrix& rows, int threads, int unroll) {
     std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols), uint8_t(threads / 64), uint8_t(unroll)};
     key.insert(key.end(), rows.v.begin(), rows.v.end());
@@ -165,6 +167,9 @@ static int compile_cubin(const Matrix& rows, int threads, int unroll, std::vecto
         "    swec_horner_body<SwecJit, false, " + U + ">(p);\n}\n"
         "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
         "    swec_horner_body<SwecJit, true, " + U + ">(p);\n}\n";
+    // one NVRTC compile at a time (the background worker and an inline caller may otherwise overlap)
+    static std::mutex& compile_mu = *new std::mutex;
+    std::lock_guard<std::mutex> compile_lock(compile_mu);
     nvrtcProgram prog = nullptr;
     if (n.create(&prog, src.c_str(), "swec_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(SWEC_ERR_JIT, "nvrtcCreateProgram failed");
