@@ -442,6 +442,14 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
         outs[size_t(i)] = fd;
     }
 
+    // The final shard size is known up front: reserve it, so the writers fill extents/pages that
+    // already exist instead of growing 14 files 8 MiB at a time (best effort; not all filesystems can).
+    if (!getenv("SWEC_NO_FALLOCATE")) {
+        const int64_t shard_size = swec_expected_shard_size(st.st_size, k, large, small);
+        if (shard_size > 0)
+            for (int fd : outs) (void)posix_fallocate(fd, 0, off_t(shard_size));
+    }
+
     Matrix rows(m, k);
     memcpy(rows.v.data(), enc->gen.row(k), rows.v.size());
     const int64_t max_chunk = int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20));

@@ -349,6 +349,25 @@ struct PendingCopy {
     size_t len;
 };
 
+// Whatever way a host-path call ends, no DMA may still be aimed at the caller's buffers when it
+// returns ("nothing is retained after a call returns", include/swec.h).
+struct DrainSlotsOnExit {
+    swec_encoder_impl* e;
+    ~DrainSlotsOnExit() {
+        for (StagingSlot& s : e->slots)
+            if (s.busy) {
+                if (s.stream) cudaStreamSynchronize(s.stream);
+                s.busy = false;
+            }
+    }
+};
+struct DeviceCounter {
+    unsigned long long* p = nullptr;
+    ~DeviceCounter() {
+        if (p) cudaFree(p);
+    }
+};
+
 bool is_pinned_or_device(const void* p, bool* is_device) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -397,11 +416,13 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
     if (rc) return rc;
     const size_t stride = e->slot_chunk;  // per-stream pitch inside a slot (>= chunk)
 
-    unsigned long long* dev_bad = nullptr;
+    DrainSlotsOnExit drain{e};
+    DeviceCounter counter;
     if (check) {
-        SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev_bad), 8));
-        SWEC_CUDA(cudaMemset(dev_bad, 0, 8));
+        SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&counter.p), 8));
+        SWEC_CUDA(cudaMemset(counter.p, 0, 8));
     }
+    unsigned long long* const dev_bad = counter.p;
 
     std::vector<std::vector<PendingCopy>> pending(e->slots.size());
     auto finish = [&](size_t si) -> int {
@@ -475,10 +496,8 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
         const int rc2 = finish(si);
         if (!rc) rc = rc2;
     }
-    if (check) {
-        if (!rc && cudaMemcpy(check, dev_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SWEC_ERR_CUDA;
-        cudaFree(dev_bad);
-    }
+    if (check && !rc && cudaMemcpy(check, dev_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "reading the mismatch counter");
     return rc;
 }
 
@@ -500,6 +519,7 @@ static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std
     const size_t chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
     if ((rc = e->ensure_slots(chunk))) return rc;
     const size_t stride = e->slot_chunk;
+    DrainSlotsOnExit drain{e};
 
     struct Unpack { uint8_t* dst; const uint8_t* src; size_t len; };
     std::vector<std::vector<Unpack>> pending(e->slots.size());
