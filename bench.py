@@ -55,23 +55,52 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML in-process every
+    ~5 ms (the timed region of 10 steps lasts ~70 ms), falling back to nvidia-smi polling."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
-    def __init__(self, index: int):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+    def __init__(self, index: int, uuid: str | None = None):
+        self.index, self.uuid = index, uuid
+        self.samples, self._stop, self._t = [], threading.Event(), None   # (sm_mhz, max_mhz, watts, {reasons})
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = None
+            if uuid:
+                try:
+                    self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+                except Exception:
+                    self._h = None
+            if self._h is None:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv, self.source = None, "nvidia-smi"
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nv:
+                    nv = self._nv
+                    sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    watts = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                    self.samples.append((sm, self._max, watts, {n for b, n in self.BITS.items() if mask & b}))
+                    self._stop.wait(0.005)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], stdout=subprocess.PIPE, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 7:
-                    self.samples.append(f)
+                    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                    self.samples.append((int(float(f[0])), int(float(f[1])), float(f[2]),
+                                         {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
             except Exception:
                 pass
             self._stop.wait(0.1)
@@ -86,12 +115,12 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted(set().union(*[s[3] for s in self.samples])) if self.samples else []
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max((s[1] for s in self.samples), default=None),
+                "power_w_max": round(max((s[2] for s in self.samples), default=0.0), 1),
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def _cpu_variants(seconds_each: float, threads: int):
@@ -250,7 +279,11 @@ def main():
     barrier()
     launches0 = L.swec_kernel_launches()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as clk:
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local, gpu_uuid) as clk:
         ev[0].record()
         for i in range(args.steps):
             step()
