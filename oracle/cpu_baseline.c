@@ -353,3 +353,63 @@ double orc_cpu_bench(int kind, int k, int r, const uint8_t *rows, size_t bytes, 
     double secs = (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
     return (double)threads * passes * k * (double)bytes / secs / 1e9;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * B3 of BASELINE.md: the reference-shaped file walk at SIMD speed — generateEcFiles exactly as
+ * ec_encoder.go:110-128,202-321 does it (one thread; per 256 KiB batch: 10 × pread, Encode,
+ * 14 × write, strictly serial), with the Encode done by the reference's own compiled kernel
+ * (kind 0) or the GFNI port (kind 1).  Returns 0 or a negative errno. */
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+
+int orc_generate_ec_files_simd(const char *base, int kind, int64_t bufsz, int64_t large, int64_t small, int k, int m)
+{
+    if (kind == 0 && !g_ref_handle) return -ENOSYS;
+    if (kind == 1 && !orc_cpu_has_gfni()) return -ENOSYS;
+    if (bufsz <= 0 || large % bufsz || small % bufsz || k + m > ORC_MAX_SHARDS) return -EINVAL;
+    char path[4096];
+    snprintf(path, sizeof path, "%s.dat", base);
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return -errno;
+    struct stat st;
+    fstat(fd, &st);
+    uint8_t *gen = (uint8_t *)malloc((size_t)(k + m) * k);
+    orc_build_matrix(k, k + m, gen);
+    const uint8_t *rows = gen + (size_t)k * k;
+    int outs[ORC_MAX_SHARDS];
+    uint8_t *bufs[ORC_MAX_SHARDS];
+    int rc = 0;
+    for (int i = 0; i < k + m; i++) {
+        snprintf(path, sizeof path, "%s.ec%02d", base, i);
+        outs[i] = open(path, O_TRUNC | O_CREAT | O_WRONLY, 0644);
+        if (outs[i] < 0) rc = -errno;
+        if (posix_memalign((void **)&bufs[i], 4096, (size_t)bufsz)) rc = -ENOMEM;
+    }
+    int64_t remaining = st.st_size, processed = 0;
+    for (int pass = 0; pass < 2 && rc == 0; pass++) {
+        int64_t block = pass == 0 ? large : small, row = block * k;
+        while (rc == 0 && (pass == 0 ? remaining >= row : remaining > 0)) {
+            for (int64_t b = 0; rc == 0 && b < block / bufsz; b++) {
+                for (int i = 0; i < k; i++) {
+                    ssize_t got = pread(fd, bufs[i], (size_t)bufsz, (off_t)(processed + b * bufsz + block * i));
+                    if (got < 0) { rc = -errno; break; }
+                    if (got < bufsz) memset(bufs[i] + got, 0, (size_t)(bufsz - got));
+                }
+                if (rc == 0)
+                    rc = orc_cpu_apply_mt(kind, k, m, rows, (const uint8_t *const *)bufs, bufs + k, (size_t)bufsz, 1, (size_t)bufsz);
+                for (int i = 0; i < k + m && rc == 0; i++)
+                    if (write(outs[i], bufs[i], (size_t)bufsz) != bufsz) rc = -EIO;
+            }
+            remaining -= row;
+            processed += row;
+        }
+    }
+    for (int i = 0; i < k + m; i++) {
+        if (outs[i] >= 0) close(outs[i]);
+        free(bufs[i]);
+    }
+    free(gen);
+    close(fd);
+    return rc;
+}

@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.orc_cpu_bench.restype = C.c_double
         L.orc_cpu_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t]
 
+        L.orc_generate_ec_files_simd.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]
+
         class Interval(C.Structure):
             _fields_ = [("block_index", C.c_int), ("inner_block_offset", C.c_int64),
                         ("size", C.c_int64), ("is_large_block", C.c_int),
@@ -209,3 +211,10 @@ def cpu_bench(kind: int, rows: np.ndarray, bytes_per_shard: int, threads: int, p
     if kind == 0 and not ref_available():
         return -1.0
     return float(lib().orc_cpu_bench(kind, k, r, rows.ctypes.data, bytes_per_shard, threads, passes, batch))
+
+
+def generate_ec_files_simd(base: str, kind: int, buffer_size=256 * 1024, large=1 << 30, small=1 << 20, k=10, m=4) -> int:
+    """The reference-shaped serial file walk with SIMD Encode (kind 0 = reference C kernel, 1 = GFNI port)."""
+    if kind == 0 and not ref_available():
+        return -38
+    return lib().orc_generate_ec_files_simd(base.encode(), kind, buffer_size, large, small, k, m)
