@@ -249,6 +249,8 @@ class FilePipeline {
         return SWEC_OK;
     }
 
+    int parallel_for(int n, const std::function<int(int)>& fn) { return io_->parallel_for(n, fn); }
+
     // wait for everything queued so far; returns the first error
     int finish() {
         std::unique_lock<std::mutex> lk(mu_);
@@ -442,20 +444,24 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
         outs[size_t(i)] = fd;
     }
 
-    // The final shard size is known up front: reserve it, so the writers fill extents/pages that
-    // already exist instead of growing 14 files 8 MiB at a time (best effort; not all filesystems can).
-    if (!getenv("SWEC_NO_FALLOCATE")) {
-        const int64_t shard_size = swec_expected_shard_size(st.st_size, k, large, small);
-        if (shard_size > 0)
-            for (int fd : outs) (void)posix_fallocate(fd, 0, off_t(shard_size));
-    }
-
     Matrix rows(m, k);
     memcpy(rows.v.data(), enc->gen.row(k), rows.v.size());
     const int64_t max_chunk = int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20));
     const size_t chunk = size_t(std::min<int64_t>(max_chunk, std::max(large, small)) + 255) & ~size_t(255);
     FilePipeline pipe(enc, rows, chunk);
     if ((rc = pipe.start())) return rc;
+
+    // The final shard size is known up front: reserve it — one I/O thread per file, because tmpfs
+    // zero-fills on fallocate — so the writers fill pages/extents that already exist instead of
+    // growing 14 files 8 MiB at a time under the filesystem's allocation lock (best effort).
+    if (!getenv("SWEC_NO_FALLOCATE")) {
+        const int64_t shard_size = swec_expected_shard_size(st.st_size, k, large, small);
+        if (shard_size > 0)
+            pipe.parallel_for(total, [&](int i) -> int {
+                (void)posix_fallocate(outs[size_t(i)], 0, off_t(shard_size));
+                return 0;
+            });
+    }
 
     int64_t remaining = st.st_size, processed = 0, shard_off = 0;
     const int64_t large_row = large * k, small_row = small * k;
@@ -584,6 +590,11 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     const size_t chunk = std::max<size_t>(256, (size_t(std::min<int64_t>(int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20)), std::max<int64_t>(todo, 1))) + 255) & ~size_t(255));
     FilePipeline pipe(enc, fused, chunk);
     if ((rc = pipe.start())) return rc;
+    if (!getenv("SWEC_NO_FALLOCATE") && todo > 0)
+        pipe.parallel_for(int(outs_idx.size()), [&](int r) -> int {
+            (void)posix_fallocate(out[size_t(outs_idx[size_t(r)])], 0, off_t(todo));
+            return 0;
+        });
     for (int64_t o = 0; rc == SWEC_OK && o < todo; o += int64_t(chunk)) {
         Item it;
         it.len = size_t(std::min<int64_t>(int64_t(chunk), todo - o));
