@@ -139,7 +139,7 @@ def _cpu_variants(seconds_each: float, threads: int):
         kinds.append((1, "gfni_port_" + ("avx512" if po.gfni_level() == 2 else "avx2")))
     res, passes_used = {}, {}
     # hyper-threads do not always help a memory-bound loop: try all logical CPUs and one per core
-    counts = sorted({threads, max(1, threads // 2)}, reverse=True)
+    counts, _quota = _thread_counts(threads)
     for kind, name in kinds:
         for tc in counts:
             probe = po.cpu_bench(kind, rows, per_shard, tc, 2)
@@ -164,7 +164,34 @@ def cpu_baseline(seconds_target: float = 12.0, threads: int | None = None):
             "sample": f"{res[best][1]} pinned threads x 10x{per_shard // MIB} MiB NUMA-local data shards, "
                       f"{passes[best]} passes each (in-memory, no disk); best of {list(res)} x thread counts",
             "variants": {k: {"GBps": v[0], "threads": v[1]} for k, v in res.items()},
-            "logical_cpus": threads, "cpu_model": _cpu_model()}
+            "logical_cpus": threads, "cpu_quota_cores": _cpu_quota_cores(), "cpu_model": _cpu_model()}
+
+
+def _cpu_quota_cores():
+    """CPU time this container may actually use (cgroup v2 cpu.max / v1 cfs quota), in cores; None = unlimited.
+    The GPU boxes report 128 logical CPUs but run under a 16-core quota — threads beyond it only throttle."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            return max(1, int(round(int(q) / int(per))))
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return max(1, int(round(q / per)))
+    except Exception:
+        pass
+    return None
+
+
+def _thread_counts(logical):
+    quota = _cpu_quota_cores()
+    cand = {logical, max(1, logical // 2)}
+    if quota:
+        cand |= {min(logical, quota), min(logical, 2 * quota)}
+    return sorted(cand, reverse=True), quota
 
 
 def _cpu_model():
@@ -198,7 +225,7 @@ def run_reference(args):
         return
     variants = {}
     for kind, label, name in kinds:
-        for tc in sorted({threads, max(1, threads // 2)}, reverse=True):
+        for tc in _thread_counts(threads)[0]:
             po.cpu_bench(kind, rows, per_shard, tc, max(1, args.warmup))      # untimed warm-up
             got = po.cpu_bench(kind, rows, per_shard, tc, args.steps * passes_per_step)
             if got > variants.get(name, (0, "", 0))[0]:
@@ -216,7 +243,7 @@ def run_reference(args):
                    "host": _cpu_model()},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": used, "kind": label, "sample": sample,
                          "variants": {k: {"GBps": round(v[0], 3), "threads": v[2]} for k, v in variants.items()},
-                         "logical_cpus": threads},
+                         "logical_cpus": threads, "cpu_quota_cores": _cpu_quota_cores()},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
