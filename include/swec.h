@@ -20,6 +20,9 @@
  *   swec_verify_ec_files        (Rust twin) verify_ec_shards   seaweed-volume/src/storage/erasure_coding/ec_encoder.rs:177-278
  *   swec_reconstruct_batch      batched ReconstructData   weed/storage/store_ec.go:482-560 (one call per interval today)
  *   swec_write_dat_file         WriteDatFile              weed/storage/erasure_coding/ec_decoder.go:176-223
+ *   swec_ec_shards_generate     VolumeEcShardsGenerate (file work)   weed/server/volume_grpc_erasure_coding.go:43-146
+ *   swec_ec_shards_rebuild      VolumeEcShardsRebuild  (file work)   weed/server/volume_grpc_erasure_coding.go:149-225
+ *   swec_ec_shards_to_volume    VolumeEcShardsToVolume (file work)   weed/server/volume_grpc_erasure_coding.go:578-668
  *   swec_locate_data            LocateData                weed/storage/erasure_coding/ec_locate.go:16-53
  *   swec_expected_shard_size    calculateExpectedShardSize   weed/storage/disk_location_ec.go:428-448
  *
@@ -50,7 +53,8 @@ typedef enum swec_status {
     SWEC_ERR_NOMEM = -5,
     SWEC_ERR_SHARD_SIZE = -6,      /* shard files of unequal length ("ec shard size expected…") */
     SWEC_ERR_NO_DEVICE = -7,       /* no usable CUDA device — there is NO CPU fallback          */
-    SWEC_ERR_JIT = -8              /* run-time kernel specialisation failed                     */
+    SWEC_ERR_JIT = -8,             /* run-time kernel specialisation failed                     */
+    SWEC_ERR_NO_LIVE_NEEDLES = -9  /* ec.decode of a volume whose index has no live entries      */
 } swec_status;
 
 typedef struct swec_encoder swec_encoder;
@@ -153,6 +157,26 @@ int swec_verify_ec_files(const char *base_file_name, const char *const *addition
 int swec_write_dat_file(const char *base_file_name, int64_t dat_file_size,
                         const char *const *shard_file_names, int data_shards,
                         int64_t large_block, int64_t small_block);
+
+/* ---- whole-volume operations: what the three EC gRPC handlers do to files, in their order --------- */
+/* VolumeEcShardsGenerate: ratio from data_base.vif when valid else 10+4; index_base.idx → .ecx FIRST;
+ * snapshot the .dat size; .dat → .ec00… on the GPU (256 KiB / 1 GiB / 1 MiB); write data_base.vif
+ * {version, datFileSize, expireAtSec, ecShardConfig}.  On any error the shard files and the .ecx are
+ * removed (the handler's deferred cleanup).  index_base NULL/"" = data_base.  needle_version 0 = read
+ * it from the .dat superblock.                                                                      */
+int swec_ec_shards_generate(const char *data_base_file_name, const char *index_base_file_name,
+                            uint32_t needle_version, uint64_t expire_at_sec, int device);
+/* VolumeEcShardsRebuild: RebuildEcFiles(data_base, additional_dirs...) then RebuildEcxFile(index_base,
+ * or data_base when index_base has no .ecx).                                                        */
+int swec_ec_shards_rebuild(const char *data_base_file_name, const char *index_base_file_name,
+                           const char *const *additional_dirs, int n_additional_dirs, int device,
+                           uint32_t *rebuilt, int *n_rebuilt);
+/* VolumeEcShardsToVolume (ec.decode): needs all data shards (data_base's directory, then
+ * additional_dirs); RebuildEcxFile → HasLiveNeedles (SWEC_ERR_NO_LIVE_NEEDLES when none) →
+ * FindDatFileSize → WriteDatFile → WriteIdxFileFromEcIndex.  No GPU work.  *dat_file_size may be NULL. */
+int swec_ec_shards_to_volume(const char *data_base_file_name, const char *index_base_file_name,
+                             const char *const *additional_dirs, int n_additional_dirs,
+                             int64_t *dat_file_size);
 
 /* ---- index files either side of the path (host only, no GPU) ---------------------------------- */
 /* WriteSortedFileFromIdx(base, ext): base.idx → base+ext (".ecx"), live entries sorted by needle id

@@ -13,7 +13,7 @@ SWEC_MAX_SHARDS = 32
 STATUS = {
     0: "SWEC_OK", -1: "SWEC_ERR_INVALID_ARG", -2: "SWEC_ERR_TOO_FEW_SHARDS", -3: "SWEC_ERR_CUDA",
     -4: "SWEC_ERR_IO", -5: "SWEC_ERR_NOMEM", -6: "SWEC_ERR_SHARD_SIZE", -7: "SWEC_ERR_NO_DEVICE",
-    -8: "SWEC_ERR_JIT",
+    -8: "SWEC_ERR_JIT", -9: "SWEC_ERR_NO_LIVE_NEEDLES",
 }
 
 
@@ -70,6 +70,10 @@ PROTOTYPES = {
     "swec_verify_ec_files": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.POINTER(C.c_int)]),
     "swec_write_dat_file": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64]),
+    "swec_ec_shards_generate": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_int]),
+    "swec_ec_shards_rebuild": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.POINTER(C.c_int)]),
+    "swec_ec_shards_to_volume": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "swec_write_sorted_file_from_idx": (C.c_int, [C.c_char_p, C.c_char_p]),
     "swec_rebuild_ecx_file": (C.c_int, [C.c_char_p]),
     "swec_write_idx_file_from_ec_index": (C.c_int, [C.c_char_p]),

@@ -376,6 +376,8 @@ class FilePipeline {
     const std::string& error_message() const { return error_msg_; }
 };
 
+}  // namespace
+
 // .vif is protobuf-JSON (weed/storage/volume_info/volume_info.go:73-95); we only need
 // ecShardConfig.{dataShards,parityShards} (weed/pb/volume_server.proto:561-577).
 bool read_vif_ratio(const std::string& path, int* ds, int* ps) {
@@ -404,6 +406,8 @@ bool read_vif_ratio(const std::string& path, int* ds, int* ps) {
     *ps = b;
     return true;
 }
+
+namespace {
 
 bool file_exists(const std::string& p) {
     struct stat st;

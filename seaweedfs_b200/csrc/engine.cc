@@ -596,6 +596,7 @@ const char* swec_strerror(int status) {
         case SWEC_ERR_SHARD_SIZE: return "shard sizes do not match";
         case SWEC_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
         case SWEC_ERR_JIT: return "run-time kernel specialisation failed";
+        case SWEC_ERR_NO_LIVE_NEEDLES: return "ec volume has no live entries";
         default: return "unknown error";
     }
 }

@@ -36,6 +36,9 @@ void* pinned_alloc(int device, size_t bytes);
 void pinned_free(void* p);
 int device_numa_node(int device);
 
+// ecShardConfig.{dataShards,parityShards} of a .vif file (ec_files.cc); false when absent/unreadable
+bool read_vif_ratio(const std::string& path, int* ds, int* ps);
+
 // device-resident multiply tables of one R×K matrix (R ≤ 4)
 struct DeviceTables {
     u32* compact = nullptr;     // [K][2][16]

@@ -249,6 +249,46 @@ def write_dat_file(base_file_name: str, dat_file_size: int, shard_file_names: li
     check(lib().swec_write_dat_file(base_file_name.encode(), dat_file_size, names, data_shards, large_block, small_block))
 
 
+# ---- whole-volume operations (the file work of the three EC gRPC handlers) --------------------------
+
+def _dirs(additional_dirs):
+    dirs = [d.encode() for d in (additional_dirs or [])]
+    return ((C.c_char_p * max(1, len(dirs)))(*dirs) if dirs else None), len(dirs)
+
+
+def volume_ec_shards_generate(data_base_file_name: str, index_base_file_name: str | None = None,
+                              needle_version: int = 0, expire_at_sec: int = 0, device: int = 0) -> None:
+    """VolumeEcShardsGenerate (volume_grpc_erasure_coding.go:43-146): .ecx first, shards, .vif; cleanup on error."""
+    check(lib().swec_ec_shards_generate(data_base_file_name.encode(),
+                                        (index_base_file_name or "").encode(), needle_version, expire_at_sec, device))
+
+
+def volume_ec_shards_rebuild(data_base_file_name: str, index_base_file_name: str | None = None,
+                             additional_dirs: list[str] | None = None, device: int = 0) -> list[int]:
+    """VolumeEcShardsRebuild (volume_grpc_erasure_coding.go:149-225): RebuildEcFiles + RebuildEcxFile."""
+    arr, n = _dirs(additional_dirs)
+    ids = (C.c_uint32 * MaxShardCount)()
+    cnt = C.c_int(0)
+    check(lib().swec_ec_shards_rebuild(data_base_file_name.encode(), (index_base_file_name or "").encode(),
+                                       arr, n, device, ids, C.byref(cnt)))
+    return list(ids[: cnt.value])
+
+
+def volume_ec_shards_to_volume(data_base_file_name: str, index_base_file_name: str | None = None,
+                               additional_dirs: list[str] | None = None) -> int:
+    """VolumeEcShardsToVolume (volume_grpc_erasure_coding.go:578-668): shards + .ecx/.ecj → .dat + .idx.
+    Returns the .dat size; raises SwecError(SWEC_ERR_NO_LIVE_NEEDLES) for an all-deleted volume."""
+    arr, n = _dirs(additional_dirs)
+    size = C.c_int64(0)
+    check(lib().swec_ec_shards_to_volume(data_base_file_name.encode(), (index_base_file_name or "").encode(),
+                                         arr, n, C.byref(size)))
+    return int(size.value)
+
+
+VolumeEcShardsGenerate, VolumeEcShardsRebuild, VolumeEcShardsToVolume = (
+    volume_ec_shards_generate, volume_ec_shards_rebuild, volume_ec_shards_to_volume)
+
+
 # ---- index files (.idx / .ecx / .ecj) --------------------------------------------------------------
 
 def write_sorted_file_from_idx(base_file_name: str, ext: str = ".ecx") -> None:

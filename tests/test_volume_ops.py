@@ -1,0 +1,229 @@
+"""Whole-volume operations — the file work of VolumeEcShardsGenerate / VolumeEcShardsRebuild /
+VolumeEcShardsToVolume (weed/server/volume_grpc_erasure_coding.go:43-225,578-668) as single C-ABI calls.
+The CPU tests cover everything that needs no GPU (ec.decode side, ordering, cleanup-on-error, error
+mapping) with shard files written by the oracle; the GPU tests run the full encode → damage → rebuild →
+decode cycle on the reference's fixture volume and compare every produced file with the oracle's."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rs_numpy as rn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_IDX = os.path.join(ROOT, "oracle", "_ref", "1.idx")
+REF_DAT = os.path.join(ROOT, "oracle", "_ref", "1.dat")
+MIB = 1 << 20
+
+
+def synthetic_volume(seed=11, needles=120, version=3):
+    """A well-formed miniature volume: 8-byte superblock (byte 0 = needle version) followed by 8-byte
+    aligned needle records, plus the .idx that indexes them (with overwrites and deletions)."""
+    rng = np.random.default_rng(seed)
+    dat = bytearray([version, 0, 0, 0, 0, 0, 0, 0])
+    idx = b""
+    for i in range(needles):
+        key = int(rng.integers(1, needles // 2))
+        size = int(rng.integers(1, 40000))
+        fixed = 16 + size + 4 + (8 if version == 3 else 0)
+        actual = fixed + (8 - fixed % 8)
+        offset = len(dat) // 8
+        dat += rng.integers(0, 256, actual, dtype=np.uint8).tobytes()
+        kind = int(rng.integers(0, 12))
+        if kind == 0:
+            idx += rn._entry(key, offset, rn.TOMBSTONE)
+        else:
+            idx += rn._entry(key, offset, size)
+    return np.frombuffer(bytes(dat), dtype=np.uint8).copy(), idx
+
+
+def lay_down_ec_volume(oracle, tmp_path, dat, idx, k=10, m=4, name="7"):
+    """What a finished ec.encode leaves on disk, written by the ORACLE (production block sizes)."""
+    base = str(tmp_path / name)
+    shards = oracle.encode_dat_image(dat, k=k, m=m)
+    for i, s in enumerate(shards):
+        s.tofile(base + ".ec%02d" % i)
+    open(base + ".ecx", "wb").write(rn.sorted_ecx_from_idx(idx))
+    return base, shards
+
+
+def read_vif(path):
+    v = json.load(open(path))
+    return {"version": int(v["version"]), "datFileSize": int(v["datFileSize"]), "expireAtSec": int(v["expireAtSec"]),
+            "ds": int(v["ecShardConfig"]["dataShards"]), "ps": int(v["ecShardConfig"]["parityShards"]),
+            "files": v["files"], "readOnly": v["readOnly"], "replication": v["replication"],
+            "bytesOffset": v["bytesOffset"]}
+
+
+# ------------------------------------------------------------------------------------------ CPU
+
+def test_ec_shards_to_volume_roundtrip(swec, oracle, tmp_path):
+    """ec.decode: shards + .ecx + .ecj → .dat + .idx.  The decoded .dat is the original up to the end of the
+    last live needle (FindDatFileSize), the .idx is .ecx plus one tombstone per journalled id."""
+    ec = swec.erasure_coding
+    dat, idx = synthetic_volume()
+    base, _ = lay_down_ec_volume(oracle, tmp_path, dat, idx)
+    ecx = rn.sorted_ecx_from_idx(idx)
+    keys = [k for k, _, _ in rn._entries(ecx)]
+    ecj = b"".join(k.to_bytes(8, "big") for k in keys[:3])
+    open(base + ".ecj", "wb").write(ecj)
+
+    size = ec.VolumeEcShardsToVolume(base)
+    folded = rn.fold_ecj_into_ecx(ecx, ecj)
+    assert open(base + ".ecx", "rb").read() == folded and not os.path.exists(base + ".ecj")
+    assert size == rn.find_dat_file_size(folded, 3)
+    out = np.fromfile(base + ".dat", dtype=np.uint8)
+    assert len(out) == size <= len(dat) and (out == dat[:size]).all()
+    assert open(base + ".idx", "rb").read() == rn.idx_from_ec_index(folded, b"")
+
+
+def test_ec_shards_to_volume_shards_on_other_disks_and_custom_ratio(swec, oracle, tmp_path):
+    """Multi-disk servers keep shards of one volume in several directories; the ratio comes from .vif."""
+    ec = swec.erasure_coding
+    dat, idx = synthetic_volume(seed=5, needles=60)
+    k, m = 6, 3
+    base, shards = lay_down_ec_volume(oracle, tmp_path, dat, idx, k=k, m=m)
+    json.dump({"version": 3, "datFileSize": str(len(dat)), "ecShardConfig": {"dataShards": k, "parityShards": m}},
+              open(base + ".vif", "w"))
+    other = tmp_path / "disk2"
+    other.mkdir()
+    for i in (1, 4):
+        os.rename(base + ".ec%02d" % i, str(other / ("7.ec%02d" % i)))
+    size = ec.VolumeEcShardsToVolume(base, additional_dirs=[str(other)])
+    out = np.fromfile(base + ".dat", dtype=np.uint8)
+    assert (out == dat[:size]).all() and size > len(dat) - 64 * 1024
+
+    os.remove(str(other / "7.ec04"))                     # a data shard is gone: the handler refuses
+    with pytest.raises(swec.SwecError) as e:
+        ec.VolumeEcShardsToVolume(base, additional_dirs=[str(other)])
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS" and "missing shard 4" in str(e.value)
+
+
+def test_ec_shards_to_volume_without_live_needles(swec, oracle, tmp_path):
+    """All needles deleted ⇒ FailedPrecondition 'no live entries' (issue-7748 path): nothing is written."""
+    ec = swec.erasure_coding
+    dat, idx = synthetic_volume(seed=2, needles=30)
+    base, _ = lay_down_ec_volume(oracle, tmp_path, dat, idx)
+    keys = [k for k, _, _ in rn._entries(rn.sorted_ecx_from_idx(idx))]
+    open(base + ".ecj", "wb").write(b"".join(k.to_bytes(8, "big") for k in keys))
+    with pytest.raises(swec.SwecError) as e:
+        ec.VolumeEcShardsToVolume(base)
+    assert e.value.name == "SWEC_ERR_NO_LIVE_NEEDLES" and "no live entries" in str(e.value)
+    assert not os.path.exists(base + ".dat") and not os.path.exists(base + ".idx")
+
+
+def test_ec_shards_generate_cleans_up_on_error(swec, tmp_path):
+    """Any failure after the .ecx was written removes the .ecx and every shard file (the handler's deferred
+    cleanup, volume_grpc_erasure_coding.go:78-87).  Here the failure is the missing GPU: device -1 has no
+    CPU fallback, so the shard step fails after .ecx and the 14 truncated shard files exist."""
+    ec = swec.erasure_coding
+    dat, idx = synthetic_volume(seed=3, needles=20)
+    base = str(tmp_path / "9")
+    dat.tofile(base + ".dat")
+    open(base + ".idx", "wb").write(idx)
+    with pytest.raises(swec.SwecError) as e:
+        ec.VolumeEcShardsGenerate(base, device=-1)
+    assert e.value.name == "SWEC_ERR_NO_DEVICE"
+    left = sorted(os.listdir(tmp_path))
+    assert left == ["9.dat", "9.idx"], left
+    # no .idx at all: fails before anything is created
+    os.remove(base + ".idx")
+    with pytest.raises(swec.SwecError) as e:
+        ec.VolumeEcShardsGenerate(base, device=-1)
+    assert e.value.name == "SWEC_ERR_IO" and sorted(os.listdir(tmp_path)) == ["9.dat"]
+
+
+def test_ec_shards_rebuild_prechecks_need_no_gpu(swec, oracle, tmp_path):
+    """Too few shards is detected before any output exists; with nothing missing only the .ecj fold runs."""
+    ec = swec.erasure_coding
+    dat, idx = synthetic_volume(seed=8, needles=25)
+    base, _ = lay_down_ec_volume(oracle, tmp_path, dat, idx)
+    keys = [k for k, _, _ in rn._entries(rn.sorted_ecx_from_idx(idx))]
+    open(base + ".ecj", "wb").write(keys[0].to_bytes(8, "big"))
+    assert ec.VolumeEcShardsRebuild(base, device=-1) == []          # nothing missing: no GPU needed
+    assert not os.path.exists(base + ".ecj")
+    assert sum(1 for _, _, s in rn._entries(open(base + ".ecx", "rb").read()) if s < 0) == 1
+    for i in range(5):
+        os.remove(base + ".ec%02d" % i)
+    with pytest.raises(swec.SwecError) as e:
+        ec.VolumeEcShardsRebuild(base, device=-1)
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS"
+    assert not any(os.path.exists(base + ".ec%02d" % i) for i in range(5))
+
+
+# ------------------------------------------------------------------------------------------ GPU
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("volume", ["fixture", "synthetic"])
+def test_volume_encode_rebuild_decode_cycle(cuda, swec, oracle, kat, tmp_path, volume):
+    """ec.encode → lose shards → ec.rebuild → ec.decode through the three handler-level calls; every file
+    is compared with the oracle's (and the fixture's shards with the committed golden digests)."""
+    import hashlib
+    ec = swec.erasure_coding
+    if volume == "fixture":
+        if not (os.path.exists(REF_DAT) and os.path.exists(REF_IDX)):
+            pytest.skip("oracle/_ref fixtures not shipped")
+        dat, idx = np.fromfile(REF_DAT, dtype=np.uint8), open(REF_IDX, "rb").read()
+    else:
+        dat, idx = synthetic_volume(seed=21, needles=400)          # ≈8 MiB: one ragged small row
+    base = str(tmp_path / "1")
+    dat.tofile(base + ".dat")
+    open(base + ".idx", "wb").write(idx)
+
+    ec.VolumeEcShardsGenerate(base, expire_at_sec=1234)
+    want = oracle.encode_dat_image(dat)
+    for i in range(14):
+        got = np.fromfile(base + ec.ToExt(i), dtype=np.uint8)
+        assert got.shape == want[i].shape and (got == want[i]).all(), f"shard {i}"
+    if volume == "fixture":
+        golden = kat["K8"]["production"]["sha256"]
+        for i in range(14):
+            assert hashlib.sha256(open(base + ec.ToExt(i), "rb").read()).hexdigest() == golden[i]
+    ecx = rn.sorted_ecx_from_idx(idx)
+    assert open(base + ".ecx", "rb").read() == ecx
+    vif = read_vif(base + ".vif")
+    assert vif == {"version": int(dat[0]), "datFileSize": len(dat), "expireAtSec": 1234, "ds": 10, "ps": 4,
+                   "files": [], "readOnly": False, "replication": "", "bytesOffset": 0}
+
+    # a server dies: four shards gone (two data, two parity); some needles deleted meanwhile
+    for i in (0, 7, 10, 13):
+        os.remove(base + ec.ToExt(i))
+    keys = [k for k, _, _ in rn._entries(ecx)]
+    ecj = b"".join(k.to_bytes(8, "big") for k in keys[:2])
+    open(base + ".ecj", "wb").write(ecj)
+    assert ec.VolumeEcShardsRebuild(base) == [0, 7, 10, 13]
+    for i in range(14):
+        assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all(), f"rebuilt shard {i}"
+    folded = rn.fold_ecj_into_ecx(ecx, ecj)
+    assert open(base + ".ecx", "rb").read() == folded
+
+    os.remove(base + ".dat")
+    os.remove(base + ".idx")
+    size = ec.VolumeEcShardsToVolume(base)
+    assert size == rn.find_dat_file_size(folded, int(dat[0]))
+    assert (np.fromfile(base + ".dat", dtype=np.uint8) == dat[:size]).all()
+    assert open(base + ".idx", "rb").read() == rn.idx_from_ec_index(folded, b"")
+
+
+@pytest.mark.gpu
+def test_volume_generate_keeps_ratio_of_existing_vif(cuda, swec, oracle, tmp_path):
+    """Regeneration keeps the EC ratio recorded in an existing .vif (volume_grpc_erasure_coding.go:61-77);
+    an invalid recorded ratio falls back to 10+4."""
+    ec = swec.erasure_coding
+    dat, idx = synthetic_volume(seed=31, needles=50)
+    base = str(tmp_path / "3")
+    dat.tofile(base + ".dat")
+    open(base + ".idx", "wb").write(idx)
+    json.dump({"version": 3, "ecShardConfig": {"dataShards": 5, "parityShards": 2}}, open(base + ".vif", "w"))
+    ec.VolumeEcShardsGenerate(base)
+    want = oracle.encode_dat_image(dat, k=5, m=2)
+    for i in range(7):
+        assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all()
+    assert not os.path.exists(base + ec.ToExt(7))
+    vif = read_vif(base + ".vif")
+    assert (vif["ds"], vif["ps"], vif["datFileSize"]) == (5, 2, len(dat))
+
+    json.dump({"version": 3, "ecShardConfig": {"dataShards": 30, "parityShards": 9}}, open(base + ".vif", "w"))
+    ec.VolumeEcShardsGenerate(base)
+    assert os.path.exists(base + ec.ToExt(13)) and read_vif(base + ".vif")["ds"] == 10
