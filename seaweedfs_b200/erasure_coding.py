@@ -50,9 +50,9 @@ class Encoder:
         self.data_shards, self.parity_shards, self.device = data_shards, parity_shards, device
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
-            lib().swec_encoder_free(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and callable(lib):        # module globals are already cleared when this runs at interpreter exit
+            lib().swec_encoder_free(h)
 
     __del__ = close
 
