@@ -487,6 +487,18 @@ def main():
             torch.cuda.synchronize()
             shards_arr = (C.c_void_p * 14)(*bufs)
             e2e_steps = max(2, min(args.steps, 5))
+            # the bound of this leg: what one H2D DMA stream reaches from the same pinned buffer (no D2H
+            # running, so an upper bound — the parity going back shares the link's control traffic)
+            probe_bytes = min(10 * n, 8 * GIB)
+            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dat[:probe_bytes].copy_(host[:probe_bytes], non_blocking=True)
+            torch.cuda.synchronize()
+            pe0.record()
+            dat[:probe_bytes].copy_(host[:probe_bytes], non_blocking=True)
+            pe1.record()
+            torch.cuda.synchronize()
+            h2d_peak = probe_bytes / (pe0.elapsed_time(pe1) / 1e3) / 1e9
+            # (host[:10n] was filled from dat[:10n], so the probe rewrote HBM with the bytes it already held)
             for _ in range(2):
                 assert L.swec_encode(enc._h, shards_arr, n) == 0
             barrier()
@@ -527,6 +539,10 @@ def main():
             e2e = {"value": round(world * e2e_steps * 10 * n / dt / 1e9, 3), "unit": UNIT,
                    "h2d_bytes_per_step": 10 * n, "d2h_bytes_per_step": 4 * n, "steps": e2e_steps,
                    "api": "swec_encode (Encoder.Encode) on pinned host shards", "volume_gib": round(10 * n / GIB, 3),
+                   "roofline": {"bound": "pcie_h2d", "achieved": round(e2e_steps * 10 * n / dt / 1e9, 2),
+                                "peak": round(h2d_peak, 2), "unit": "GB/s per GPU",
+                                "frac": round(e2e_steps * 10 * n / dt / 1e9 / h2d_peak, 4),
+                                "peak_source": "H2D-only DMA of the same pinned buffer, timed in this run"},
                    "check": e2e_check}
             L.swec_free_pinned(raw)
     barrier()
