@@ -108,6 +108,15 @@ typedef struct swec_reconstruct_item {
     int data_only;
 } swec_reconstruct_item;
 int swec_reconstruct_batch(swec_encoder *enc, const swec_reconstruct_item *items, int n_items);
+/* One call, several GPUs: the byte-column range [0, shard_len) is cut into n_encs contiguous pieces and
+ * piece g goes through encs[g] (one handle per GPU, created with swec_encoder_new(k, m, device_g)), all
+ * pieces concurrently, each over its own GPU's PCIe link.  Columns are independent, so the result is
+ * byte-identical to swec_encode / swec_reconstruct on one handle; there is no inter-GPU traffic.  This
+ * is the second axis of independence of SURVEY §8e (the first — whole volumes round-robin over GPUs —
+ * needs no API: give each concurrent volume a handle on another device).                            */
+int swec_encode_multi(swec_encoder *const *encs, int n_encs, uint8_t *const *shards, size_t shard_len);
+int swec_reconstruct_multi(swec_encoder *const *encs, int n_encs, uint8_t *const *shards,
+                           const uint8_t *present, size_t shard_len, int data_only);
 /* *ok = 1 iff the parity shards match the data shards.                                         */
 int swec_verify(swec_encoder *enc, uint8_t *const *shards, size_t shard_len, int *ok);
 

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include <execinfo.h>
 #include <signal.h>
@@ -774,6 +775,90 @@ int swec_reconstruct_batch(swec_encoder* e, const swec_reconstruct_item* items, 
         if (rc) return rc;
     }
     return SWEC_OK;
+}
+
+// ---- one call, several GPUs: column ranges are independent (parity_p[x] depends only on data_*[x]),
+// so a host-buffer call can be cut into contiguous byte ranges, one per encoder handle (= per GPU), each
+// range travelling over its own GPU's PCIe link through that handle's staging ring.  No collective.
+
+}  // extern "C"
+
+namespace {
+
+template <class Fn>  // fn(g, offset, len) → status, run concurrently for every non-empty range
+int split_columns(int n_encs, size_t n, Fn&& fn) {
+    // 4 KiB granularity keeps every range page- and 16-byte aligned relative to the caller's buffers
+    const size_t gran = 4096;
+    const size_t units = (n + gran - 1) / gran;
+    std::vector<size_t> begin(size_t(n_encs) + 1, 0);
+    for (int g = 0; g <= n_encs; g++) begin[size_t(g)] = std::min(n, units * size_t(g) / size_t(n_encs) * gran);
+    begin[size_t(n_encs)] = n;
+    std::vector<int> rc(size_t(n_encs), SWEC_OK);
+    std::vector<std::string> msg(static_cast<size_t>(n_encs));
+    std::vector<std::thread> threads;
+    for (int g = 0; g < n_encs; g++) {
+        const size_t off = begin[size_t(g)], len = begin[size_t(g) + 1] - off;
+        if (!len) continue;
+        threads.emplace_back([&, g, off, len] {
+            rc[size_t(g)] = fn(g, off, len);
+            if (rc[size_t(g)]) msg[size_t(g)] = last_error();  // thread-local: carry it to the caller's thread
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int g = 0; g < n_encs; g++)
+        if (rc[size_t(g)]) return fail(rc[size_t(g)], msg[size_t(g)]);
+    return SWEC_OK;
+}
+
+int check_group(swec_encoder* const* encs, int n_encs) {
+    if (!encs || n_encs <= 0 || n_encs > 64) return fail(SWEC_ERR_INVALID_ARG, "need 1..64 encoder handles");
+    for (int g = 0; g < n_encs; g++) {
+        if (!encs[g]) return fail(SWEC_ERR_INVALID_ARG, "NULL encoder handle");
+        if (encs[g]->k != encs[0]->k || encs[g]->m != encs[0]->m)
+            return fail(SWEC_ERR_INVALID_ARG, "encoder handles of one group must share the EC ratio");
+        for (int h = 0; h < g; h++)
+            if (encs[h] == encs[g]) return fail(SWEC_ERR_INVALID_ARG, "the same encoder handle appears twice (its staging ring serialises)");
+    }
+    return SWEC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int swec_encode_multi(swec_encoder* const* encs, int n_encs, uint8_t* const* shards, size_t n) {
+    int rc = check_group(encs, n_encs);
+    if (rc) return rc;
+    if (!shards) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    if (n == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0 (ErrShardNoData)");
+    const int total = encs[0]->k + encs[0]->m;
+    for (int i = 0; i < total; i++)
+        if (!shards[i]) return fail(SWEC_ERR_INVALID_ARG, "NULL shard");
+    return split_columns(n_encs, n, [&](int g, size_t off, size_t len) {
+        uint8_t* sub[SWEC_MAX_SHARDS];
+        for (int i = 0; i < total; i++) sub[i] = shards[i] + off;
+        return swec_encode(encs[g], sub, len);
+    });
+}
+
+int swec_reconstruct_multi(swec_encoder* const* encs, int n_encs, uint8_t* const* shards, const uint8_t* present,
+                           size_t n, int data_only) {
+    int rc = check_group(encs, n_encs);
+    if (rc) return rc;
+    if (!shards || !present) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    const int k = encs[0]->k, total = k + encs[0]->m;
+    int npresent = 0;
+    for (int i = 0; i < total; i++) npresent += present[i] ? 1 : 0;
+    if (npresent == total) return SWEC_OK;
+    if (npresent < k) return fail(SWEC_ERR_TOO_FEW_SHARDS, "fewer than data_shards shards present");
+    if (n == 0) return fail(SWEC_ERR_INVALID_ARG, "shard_len is 0 (ErrShardNoData)");
+    for (int i = 0; i < total; i++)
+        if (!present[i] && (i < k || !data_only) && !shards[i]) return fail(SWEC_ERR_INVALID_ARG, "missing shard has no buffer");
+    return split_columns(n_encs, n, [&](int g, size_t off, size_t len) {
+        uint8_t* sub[SWEC_MAX_SHARDS];
+        for (int i = 0; i < total; i++) sub[i] = shards[i] ? shards[i] + off : nullptr;
+        return swec_reconstruct(encs[g], sub, present, len, data_only);
+    });
 }
 
 int swec_verify(swec_encoder* e, uint8_t* const* shards, size_t n, int* ok) {

@@ -174,6 +174,44 @@ class Encoder:
     Encode, Reconstruct, ReconstructData, Verify = encode, reconstruct, reconstruct_data, verify
 
 
+class EncoderGroup:
+    """Several Encoder handles (one per GPU) behind the Encoder interface: every host-buffer call is split
+    by byte-column range across the handles (swec_encode_multi / swec_reconstruct_multi)."""
+
+    def __init__(self, data_shards: int, parity_shards: int, devices: list[int]):
+        self.encoders = [Encoder(data_shards, parity_shards, d) for d in devices]
+        self.data_shards, self.parity_shards = data_shards, parity_shards
+        self._arr = (C.c_void_p * len(self.encoders))(*[e._h for e in self.encoders])
+
+    @property
+    def total_shards(self) -> int:
+        return self.data_shards + self.parity_shards
+
+    def close(self) -> None:
+        for e in self.encoders:
+            e.close()
+        self.encoders = []
+
+    def encode(self, shards: list[np.ndarray]) -> None:
+        n = self.encoders[0]._check_shards(shards, allow_missing=False)
+        check(lib().swec_encode_multi(self._arr, len(self.encoders), _ptrs(shards), n))
+
+    def reconstruct(self, shards: list, data_only: bool = False) -> None:
+        e0 = self.encoders[0]
+        n = e0._check_shards(shards, allow_missing=True)
+        present = np.array([s is not None and len(s) > 0 for s in shards], dtype=np.uint8)
+        if present.sum() < self.data_shards:
+            raise SwecError(-2, "too few shards given (ErrTooFewShards)")
+        for i in range(self.total_shards):
+            if not present[i] and (i < self.data_shards or not data_only):
+                shards[i] = np.zeros(n, dtype=np.uint8)
+        bufs = [s if s is not None and len(s) else None for s in shards]
+        check(lib().swec_reconstruct_multi(self._arr, len(self.encoders), _ptrs(bufs), present.ctypes.data, n,
+                                           int(data_only)))
+
+    Encode, Reconstruct = encode, reconstruct
+
+
 @dataclass
 class ECContext:
     """ec_context.go:11-46"""

@@ -142,6 +142,30 @@ def test_argument_validation(swec, tmp_path):
     assert e.value.name == "SWEC_ERR_IO"
 
 
+def test_multi_handle_argument_validation(swec):
+    """The column-split calls validate the group before touching a device."""
+    ec = swec.erasure_coding
+    L = swec.lib()
+    a, b, c = ec.Encoder(10, 4, device=-1), ec.Encoder(10, 4, device=-1), ec.Encoder(6, 3, device=-1)
+    shards = [np.zeros(8192, dtype=np.uint8) for _ in range(14)]
+    ptrs = (C.c_void_p * 14)(*[s.ctypes.data for s in shards])
+    present = (C.c_uint8 * 14)(*([0] + [1] * 13))
+
+    def group(*encs):
+        return (C.c_void_p * len(encs))(*[e._h for e in encs]), len(encs)
+    assert L.swec_encode_multi(*group(a, a), ptrs, 8192) == -1            # same handle twice
+    assert L.swec_encode_multi(*group(a, c), ptrs, 8192) == -1            # mixed ratios
+    assert L.swec_encode_multi(None, 0, ptrs, 8192) == -1
+    assert L.swec_encode_multi(*group(a, b), ptrs, 0) == -1               # ErrShardNoData
+    assert L.swec_encode_multi(*group(a, b), ptrs, 8192) == -7            # no device: loud, no fallback
+    assert b"no CPU fallback" in L.swec_last_error()                      # detail crossed from the worker thread
+    assert L.swec_reconstruct_multi(*group(a, b), ptrs, present, 8192, 0) == -7
+    few = (C.c_uint8 * 14)(*([0] * 5 + [1] * 9))
+    assert L.swec_reconstruct_multi(*group(a, b), ptrs, few, 8192, 0) == -2
+    allp = (C.c_uint8 * 14)(*([1] * 14))
+    assert L.swec_reconstruct_multi(*group(a, b), ptrs, allp, 8192, 0) == 0   # nothing to do
+
+
 def test_rebuild_prechecks_need_no_gpu(swec, tmp_path):
     """generateMissingEcFiles bails out before creating outputs when < k shards exist (ec_encoder.go:172-175)."""
     ec = swec.erasure_coding

@@ -89,3 +89,32 @@ def test_one_process_many_gpus(cuda, swec, oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n", [1, 4095, 4096 * 3 + 17, 9_000_000 + 3])
+def test_one_call_split_over_several_handles(cuda, swec, oracle, n):
+    """swec_encode_multi / swec_reconstruct_multi cut the byte-column range across encoder handles — one per
+    GPU when the box has several; on a single-GPU box three handles on device 0 exercise the same split
+    (ranges of 4 KiB units, empty ranges when n is tiny).  Result = the single-handle call, bit for bit."""
+    torch = cuda
+    ec = swec.erasure_coding
+    ngpu = torch.cuda.device_count()
+    devices = list(range(ngpu)) if ngpu >= 2 else [0, 0, 0]
+    grp = ec.EncoderGroup(10, 4, devices)
+    rng = np.random.default_rng(n)
+    data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+    want = oracle.encode(10, 4, data)
+    shards = [d.copy() for d in data] + [np.full(n, 0x77, dtype=np.uint8) for _ in range(4)]
+    grp.encode(shards)
+    assert all((a == b).all() for a, b in zip(shards[:10], data))
+    assert all((a == b).all() for a, b in zip(shards[10:], want))
+    holes = [s.copy() for s in shards]
+    for i in (1, 6, 10, 12):
+        holes[i] = None
+    grp.reconstruct(holes)
+    assert all((a == b).all() for a, b in zip(holes, shards))
+    holes = [s.copy() for s in shards]
+    holes[4] = holes[13] = None
+    grp.reconstruct(holes, data_only=True)
+    assert (holes[4] == shards[4]).all() and holes[13] is None
+    grp.close()
