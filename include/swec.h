@@ -23,6 +23,7 @@
  *   swec_ec_shards_generate     VolumeEcShardsGenerate (file work)   weed/server/volume_grpc_erasure_coding.go:43-146
  *   swec_ec_shards_rebuild      VolumeEcShardsRebuild  (file work)   weed/server/volume_grpc_erasure_coding.go:149-225
  *   swec_ec_shards_to_volume    VolumeEcShardsToVolume (file work)   weed/server/volume_grpc_erasure_coding.go:578-668
+ *   swec_read_ec_needles        Store.ReadEcShardNeedle (local shards, batched)   weed/storage/store_ec.go:252-355,482-560
  *   swec_locate_data            LocateData                weed/storage/erasure_coding/ec_locate.go:16-53
  *   swec_expected_shard_size    calculateExpectedShardSize   weed/storage/disk_location_ec.go:428-448
  *
@@ -54,7 +55,9 @@ typedef enum swec_status {
     SWEC_ERR_SHARD_SIZE = -6,      /* shard files of unequal length ("ec shard size expected…") */
     SWEC_ERR_NO_DEVICE = -7,       /* no usable CUDA device — there is NO CPU fallback          */
     SWEC_ERR_JIT = -8,             /* run-time kernel specialisation failed                     */
-    SWEC_ERR_NO_LIVE_NEEDLES = -9  /* ec.decode of a volume whose index has no live entries      */
+    SWEC_ERR_NO_LIVE_NEEDLES = -9, /* ec.decode of a volume whose index has no live entries      */
+    SWEC_ERR_NOT_FOUND = -10,      /* needle id not in .ecx (erasure_coding.NotFoundError)       */
+    SWEC_ERR_DELETED = -11         /* needle is tombstoned or journalled (storage.ErrorDeleted)  */
 } swec_status;
 
 typedef struct swec_encoder swec_encoder;
@@ -186,6 +189,31 @@ int swec_ec_shards_rebuild(const char *data_base_file_name, const char *index_ba
 int swec_ec_shards_to_volume(const char *data_base_file_name, const char *index_base_file_name,
                              const char *const *additional_dirs, int n_additional_dirs,
                              int64_t *dat_file_size);
+
+/* Store.ReadEcShardNeedle for MANY needles of one EC volume whose shard files are local (data_base's
+ * directory, then additional_dirs) — weed/storage/store_ec.go:252-355,482-560: find each needle in .ecx
+ * (journalled ids read as deleted), LocateData its record through the two-tier layout (shard size from
+ * .vif's datFileSize, else shard file size - 1), pread every interval whose shard file is present and
+ * recover the others from the same interval of all remaining shards with ReconstructData.  All
+ * recoveries of the call go to the GPU as ONE swec_reconstruct_batch; with every needed shard present the
+ * call does no GPU work at all.  buf receives the raw record bytes exactly as the reference's `bytes`
+ * (which over-reads: GetActualSize is applied twice, ec_volume.go:395,414); parsing them is the storage
+ * engine's business.  Per-needle outcome in status: SWEC_OK, SWEC_ERR_NOT_FOUND, SWEC_ERR_DELETED,
+ * SWEC_ERR_TOO_FEW_SHARDS, or SWEC_ERR_INVALID_ARG when capacity < the n_bytes reported back.        */
+typedef struct swec_needle_read {
+    uint64_t needle_id;            /* in  */
+    uint8_t *buf;                  /* in  */
+    size_t capacity;               /* in  */
+    int64_t offset;                /* out: byte offset of the record in the .dat                  */
+    int32_t size;                  /* out: Size field of the index entry (negative = deleted)      */
+    int32_t status;                /* out */
+    size_t n_bytes;                /* out: bytes stored in buf (or needed, on SWEC_ERR_INVALID_ARG) */
+    int32_t n_recovered_intervals; /* out: intervals that were reconstructed rather than read      */
+    int32_t reserved;
+} swec_needle_read;
+int swec_read_ec_needles(const char *data_base_file_name, const char *index_base_file_name,
+                         const char *const *additional_dirs, int n_additional_dirs,
+                         swec_needle_read *reads, int n_reads, int device);
 
 /* ---- index files either side of the path (host only, no GPU) ---------------------------------- */
 /* WriteSortedFileFromIdx(base, ext): base.idx → base+ext (".ecx"), live entries sorted by needle id

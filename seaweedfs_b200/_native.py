@@ -14,6 +14,7 @@ STATUS = {
     0: "SWEC_OK", -1: "SWEC_ERR_INVALID_ARG", -2: "SWEC_ERR_TOO_FEW_SHARDS", -3: "SWEC_ERR_CUDA",
     -4: "SWEC_ERR_IO", -5: "SWEC_ERR_NOMEM", -6: "SWEC_ERR_SHARD_SIZE", -7: "SWEC_ERR_NO_DEVICE",
     -8: "SWEC_ERR_JIT", -9: "SWEC_ERR_NO_LIVE_NEEDLES",
+    -10: "SWEC_ERR_NOT_FOUND", -11: "SWEC_ERR_DELETED",
 }
 
 
@@ -33,6 +34,12 @@ class Interval(C.Structure):
     _fields_ = [("block_index", C.c_int32), ("is_large_block", C.c_int32),
                 ("inner_block_offset", C.c_int64), ("size", C.c_int64),
                 ("large_block_rows_count", C.c_int32), ("reserved", C.c_int32)]
+
+
+class NeedleRead(C.Structure):
+    _fields_ = [("needle_id", C.c_uint64), ("buf", C.c_void_p), ("capacity", C.c_size_t), ("offset", C.c_int64),
+                ("size", C.c_int32), ("status", C.c_int32), ("n_bytes", C.c_size_t),
+                ("n_recovered_intervals", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name → (restype, argtypes); kept in step with include/swec.h (tests/test_abi.py checks both ways)
@@ -76,6 +83,7 @@ PROTOTYPES = {
     "swec_ec_shards_rebuild": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                          C.POINTER(C.c_int)]),
     "swec_ec_shards_to_volume": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
+    "swec_read_ec_needles": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(NeedleRead), C.c_int, C.c_int]),
     "swec_write_sorted_file_from_idx": (C.c_int, [C.c_char_p, C.c_char_p]),
     "swec_rebuild_ecx_file": (C.c_int, [C.c_char_p]),
     "swec_write_idx_file_from_ec_index": (C.c_int, [C.c_char_p]),

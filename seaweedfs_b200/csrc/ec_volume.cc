@@ -3,6 +3,9 @@
 //   swec_ec_shards_generate    VolumeEcShardsGenerate   weed/server/volume_grpc_erasure_coding.go:43-146
 //   swec_ec_shards_rebuild     VolumeEcShardsRebuild    weed/server/volume_grpc_erasure_coding.go:149-225
 //   swec_ec_shards_to_volume   VolumeEcShardsToVolume   weed/server/volume_grpc_erasure_coding.go:578-668
+//   swec_read_ec_needles       Store.ReadEcShardNeedle + readEcShardIntervals + readOneEcShardInterval +
+//                              recoverOneRemoteEcShardInterval, on local shard files, batched
+//                                                       weed/storage/store_ec.go:252-355,482-560
 // Everything the handlers do to FILES is here, in the reference's order (.ecx before the shards, the
 // .dat size snapshot before encoding, .vif last, partial outputs removed on any error); what they do
 // to the server's in-memory state (volume lookup, maintenance mode, disk-location scan, compaction)
@@ -14,9 +17,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cctype>
 #include <cinttypes>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -90,6 +95,52 @@ void ratio_from_vif(const std::string& data_base, int* k, int* m) {
         *m = 4;
     }
 }
+
+// A numeric field of a protobuf-JSON .vif (64-bit integers are rendered as strings); false when absent.
+bool vif_number(const std::string& txt, const char* key, int64_t* out) {
+    const std::string k = std::string("\"") + key + "\"";
+    const size_t p = txt.find(k);
+    if (p == std::string::npos) return false;
+    size_t q = txt.find(':', p + k.size());
+    if (q == std::string::npos) return false;
+    q++;
+    while (q < txt.size() && (txt[q] == ' ' || txt[q] == '"' || txt[q] == '\t' || txt[q] == '\n')) q++;
+    if (q >= txt.size() || !(isdigit((unsigned char)txt[q]) || txt[q] == '-')) return false;
+    *out = strtoll(txt.c_str() + q, nullptr, 10);
+    return true;
+}
+
+bool slurp(const std::string& path, std::string* out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t n;
+    out->clear();
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+    fclose(f);
+    return true;
+}
+
+uint64_t be64(const uint8_t* p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+    return v;
+}
+uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
+
+// GetActualSize (needle/needle_read.go:292-294, needle_read_tail.go:36-49)
+int64_t needle_actual_size(int64_t size, int version) {
+    const int64_t fixed = 16 + size + 4 + (version == 3 ? 8 : 0);
+    return fixed + (8 - fixed % 8);
+}
+
+struct FdCloser {
+    std::vector<int> fds;
+    ~FdCloser() {
+        for (int fd : fds)
+            if (fd >= 0) close(fd);
+    }
+};
 
 }  // namespace
 }  // namespace swec
@@ -198,6 +249,206 @@ int swec_ec_shards_to_volume(const char* data_base, const char* index_base, cons
     if ((rc = swec_write_dat_file(db.c_str(), size, cnames.data(), k, int64_t(1) << 30, int64_t(1) << 20))) return rc;
     if ((rc = swec_write_idx_file_from_ec_index(ib.c_str()))) return rc;
     if (dat_file_size) *dat_file_size = size;
+    return SWEC_OK;
+}
+
+int swec_read_ec_needles(const char* data_base, const char* index_base, const char* const* additional_dirs,
+                         int n_additional_dirs, swec_needle_read* reads, int n_reads, int device) {
+    if (!data_base || (n_reads > 0 && !reads) || (n_additional_dirs > 0 && !additional_dirs))
+        return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    const std::string db(data_base);
+    std::string ib(index_base && *index_base ? index_base : data_base);
+    if (!is_file(ib + ".ecx")) ib = db;  // NewEcVolume falls back to the data directory (ec_volume.go:72-85)
+
+    // ---- what NewEcVolume loads: ratio, needle version and datFileSize from .vif (ec_volume.go:114-154)
+    int k, m;
+    ratio_from_vif(db, &k, &m);
+    const int total = k + m;
+    int version = 3;
+    int64_t dat_file_size = 0;
+    {
+        std::string vif;
+        if (slurp(db + ".vif", &vif) || slurp(ib + ".vif", &vif)) {
+            int64_t v = 0;
+            if (vif_number(vif, "version", &v) && v > 0) version = int(v);
+            if (vif_number(vif, "datFileSize", &v)) dat_file_size = v;
+        }
+    }
+    // ---- local shards (data_base's directory, then the other disks)
+    std::string base_copy(db);
+    const std::string base_name = basename(&base_copy[0]);
+    FdCloser fds;
+    std::vector<int> shard_fd(size_t(total), -1);
+    int64_t ecd_file_size = -1;
+    int nlocal = 0;
+    for (int i = 0; i < total; i++) {
+        std::string path = db + ext_of(i);
+        if (!is_file(path)) {
+            path.clear();
+            for (int d = 0; d < n_additional_dirs; d++) {
+                const std::string cand = std::string(additional_dirs[d]) + "/" + base_name + ext_of(i);
+                if (is_file(cand)) {
+                    path = cand;
+                    break;
+                }
+            }
+        }
+        if (path.empty()) continue;
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) continue;  // unreadable = not local; the interval is recovered from the others
+        fds.fds.push_back(fd);
+        shard_fd[size_t(i)] = fd;
+        nlocal++;
+        if (ecd_file_size < 0) {
+            struct stat st;
+            if (fstat(fd, &st) == 0) ecd_file_size = st.st_size;
+        }
+    }
+    if (nlocal == 0) return fail(SWEC_ERR_TOO_FEW_SHARDS, "ec shard " + db + " not found");
+    // LocateEcShardNeedleInterval: .vif's datFileSize is authoritative; old volumes fall back to the
+    // shard file size minus one (ec_volume.go:399-417)
+    const int64_t shard_dat_size = dat_file_size > 0 ? dat_file_size / k : ecd_file_size - 1;
+    const int64_t large = int64_t(1) << 30, small = int64_t(1) << 20;
+
+    // ---- the sealed index plus the deletion journal (FindNeedleFromEcx, ec_volume.go:419-429)
+    std::string ecx, ecj;
+    if (!slurp(ib + ".ecx", &ecx)) return fail(SWEC_ERR_IO, "cannot open ec volume index " + ib + ".ecx: " + strerror(errno));
+    slurp(ib + ".ecj", &ecj);
+    const uint8_t* ex = reinterpret_cast<const uint8_t*>(ecx.data());
+    const int64_t entries = int64_t(ecx.size()) / 16;
+    auto journalled = [&](uint64_t id) {
+        for (size_t off = 0; off + 8 <= ecj.size(); off += 8)
+            if (be64(reinterpret_cast<const uint8_t*>(ecj.data()) + off) == id) return true;
+        return false;
+    };
+
+    // ---- pass 1: locate every needle, read what is local, collect what must be recovered
+    struct Recover {
+        int read_idx;
+        size_t buf_off, len;
+        int shard;
+        std::vector<std::vector<uint8_t>> bufs;  // total entries; empty = not available
+        std::vector<uint8_t*> ptrs;
+        std::vector<uint8_t> present;
+    };
+    std::vector<Recover> recs;
+    for (int r = 0; r < n_reads; r++) {
+        swec_needle_read& rd = reads[r];
+        rd.offset = 0;
+        rd.size = 0;
+        rd.n_bytes = 0;
+        rd.n_recovered_intervals = 0;
+        rd.status = SWEC_OK;
+        int64_t lo = 0, hi = entries, found = -1;  // SearchNeedleFromSortedIndex (ec_volume.go:431-458)
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            const uint64_t key = be64(ex + mid * 16);
+            if (key == rd.needle_id) {
+                found = mid;
+                break;
+            }
+            if (key < rd.needle_id) lo = mid + 1;
+            else hi = mid;
+        }
+        if (found < 0) {
+            rd.status = SWEC_ERR_NOT_FOUND;
+            continue;
+        }
+        const int64_t offset = int64_t(be32(ex + found * 16 + 8)) * 8;  // Offset.ToActualOffset (offset_4bytes.go)
+        int32_t size = int32_t(be32(ex + found * 16 + 12));
+        if (journalled(rd.needle_id)) size = -1;  // TombstoneFileSize
+        rd.offset = offset;
+        rd.size = size;
+        if (size < 0) {  // Size.IsDeleted
+            rd.status = SWEC_ERR_DELETED;
+            continue;
+        }
+        // LocateEcShardNeedle passes GetActualSize(size) to LocateEcShardNeedleInterval, which applies
+        // GetActualSize AGAIN (ec_volume.go:395,414): the reference reads a little past the record.  Kept,
+        // because ReadEcShardNeedle returns len(bytes) and n.ReadBytes only parses the front.
+        const int64_t want = needle_actual_size(needle_actual_size(size, version), version);
+        if (!rd.buf || size_t(want) > rd.capacity) {
+            rd.n_bytes = size_t(want);
+            rd.status = SWEC_ERR_INVALID_ARG;
+            continue;
+        }
+        swec_interval ivs[64];
+        const int niv = swec_locate_data(large, small, shard_dat_size, offset, want, k, ivs, 64);
+        if (niv < 0) {
+            rd.status = niv;
+            continue;
+        }
+        size_t pos = 0;
+        for (int j = 0; j < niv && rd.status == SWEC_OK; j++) {
+            int sid = 0;
+            int64_t soff = 0;
+            swec_interval_to_shard(&ivs[j], large, small, k, &sid, &soff);
+            const size_t len = size_t(ivs[j].size);
+            bool ok = false;
+            if (shard_fd[size_t(sid)] >= 0) {  // readLocalEcShardInterval (store_ec.go:407-422): all or nothing
+                const ssize_t got = pread(shard_fd[size_t(sid)], rd.buf + pos, len, off_t(soff));
+                ok = got == ssize_t(len);
+            }
+            if (!ok) {  // recoverOneRemoteEcShardInterval, with "remote" = every other local shard file
+                Recover rc;
+                rc.read_idx = r;
+                rc.buf_off = pos;
+                rc.len = len;
+                rc.shard = sid;
+                rc.bufs.resize(size_t(total));
+                rc.ptrs.assign(size_t(total), nullptr);
+                rc.present.assign(size_t(total), 0);
+                int have = 0;
+                for (int i = 0; i < total; i++) {
+                    if (i == sid || shard_fd[size_t(i)] < 0) continue;
+                    rc.bufs[size_t(i)].resize(len);
+                    if (pread(shard_fd[size_t(i)], rc.bufs[size_t(i)].data(), len, off_t(soff)) == ssize_t(len)) {
+                        rc.present[size_t(i)] = 1;
+                        have++;
+                    } else {
+                        rc.bufs[size_t(i)].clear();  // nRead != len(buf): not available
+                    }
+                }
+                if (have < k) {
+                    rd.status = SWEC_ERR_TOO_FEW_SHARDS;
+                    set_last_error("cannot recover shard " + std::to_string(sid) + ": only " + std::to_string(have) +
+                                   " shards available, need at least " + std::to_string(k));
+                    break;
+                }
+                for (int i = 0; i < k; i++)  // ReconstructData fills every missing DATA shard
+                    if (!rc.present[size_t(i)]) rc.bufs[size_t(i)].resize(len);
+                for (int i = 0; i < total; i++) rc.ptrs[size_t(i)] = rc.bufs[size_t(i)].empty() ? nullptr : rc.bufs[size_t(i)].data();
+                recs.push_back(std::move(rc));
+                rd.n_recovered_intervals++;
+            }
+            pos += len;
+        }
+        if (rd.status == SWEC_OK) rd.n_bytes = pos;
+    }
+
+    // ---- pass 2: every interval that needs the arithmetic, in ONE batched ReconstructData on the GPU
+    if (!recs.empty()) {
+        swec_encoder* enc = nullptr;
+        int rc = swec_encoder_new(k, m, device, &enc);
+        if (rc) return rc;
+        std::unique_ptr<swec_encoder, void (*)(swec_encoder*)> guard(enc, swec_encoder_free);
+        std::vector<swec_reconstruct_item> items(recs.size());
+        for (size_t j = 0; j < recs.size(); j++) {
+            // the moves above kept the heap blocks, but rebuild the pointer table to be safe
+            for (int i = 0; i < total; i++) recs[j].ptrs[size_t(i)] = recs[j].bufs[size_t(i)].empty() ? nullptr : recs[j].bufs[size_t(i)].data();
+            items[j].shards = recs[j].ptrs.data();
+            items[j].present = recs[j].present.data();
+            items[j].shard_len = recs[j].len;
+            items[j].data_only = 1;
+        }
+        rc = swec_reconstruct_batch(enc, items.data(), int(items.size()));
+        if (rc) return rc;
+        for (const Recover& rcv : recs) {
+            swec_needle_read& rd = reads[rcv.read_idx];
+            if (rd.status != SWEC_OK) continue;
+            memcpy(rd.buf + rcv.buf_off, rcv.bufs[size_t(rcv.shard)].data(), rcv.len);
+        }
+    }
     return SWEC_OK;
 }
 

@@ -598,6 +598,8 @@ const char* swec_strerror(int status) {
         case SWEC_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
         case SWEC_ERR_JIT: return "run-time kernel specialisation failed";
         case SWEC_ERR_NO_LIVE_NEEDLES: return "ec volume has no live entries";
+        case SWEC_ERR_NOT_FOUND: return "needle not found";
+        case SWEC_ERR_DELETED: return "needle already deleted";
         default: return "unknown error";
     }
 }

@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._native import Interval, ReconstructItem, SwecError, check, lib
+from ._native import STATUS, Interval, NeedleRead, ReconstructItem, SwecError, check, lib
 
 DataShardsCount = 10                               # ec_encoder.go:20
 ParityShardsCount = 4                              # ec_encoder.go:21
@@ -323,6 +323,25 @@ def volume_ec_shards_to_volume(data_base_file_name: str, index_base_file_name: s
     return int(size.value)
 
 
+def read_ec_shard_needles(data_base_file_name: str, needle_ids: list[int], index_base_file_name: str | None = None,
+                          additional_dirs: list[str] | None = None, device: int = 0, capacity: int = 1 << 20):
+    """Store.ReadEcShardNeedle for many needles at once (store_ec.go:252-355): returns one dict per id with
+    status name, offset, size, the raw record bytes and how many intervals had to be reconstructed."""
+    arr, n = _dirs(additional_dirs)
+    reads = (NeedleRead * len(needle_ids))()
+    bufs = []
+    for r, nid in zip(reads, needle_ids):
+        b = np.zeros(capacity, dtype=np.uint8)
+        bufs.append(b)
+        r.needle_id, r.buf, r.capacity = nid, b.ctypes.data, capacity
+    check(lib().swec_read_ec_needles(data_base_file_name.encode(), (index_base_file_name or "").encode(), arr, n,
+                                     reads, len(needle_ids), device))
+    return [{"id": r.needle_id, "status": STATUS.get(r.status, str(r.status)), "offset": r.offset, "size": r.size,
+             "bytes": b[: r.n_bytes].copy() if r.status == 0 else None, "n_bytes": r.n_bytes,
+             "recovered_intervals": r.n_recovered_intervals} for r, b in zip(reads, bufs)]
+
+
+ReadEcShardNeedles = read_ec_shard_needles
 VolumeEcShardsGenerate, VolumeEcShardsRebuild, VolumeEcShardsToVolume = (
     volume_ec_shards_generate, volume_ec_shards_rebuild, volume_ec_shards_to_volume)
 

@@ -36,7 +36,7 @@ static int run_abi(void) {
         {129, 150, 175, 184, 210, 196, 254, 232, 3, 2}, {150, 129, 184, 175, 196, 210, 232, 254, 2, 3},
         {191, 214, 98, 10, 6, 111, 223, 183, 5, 4},     {214, 191, 10, 98, 111, 6, 183, 223, 4, 5}};
     CHECK(strstr(swec_version(), "swec") != NULL);
-    for (int s = 0; s >= SWEC_ERR_NO_LIVE_NEEDLES; s--) CHECK(strcmp(swec_strerror(s), "unknown error") != 0);
+    for (int s = 0; s >= SWEC_ERR_DELETED; s--) CHECK(strcmp(swec_strerror(s), "unknown error") != 0);
     CHECK(strcmp(swec_strerror(-100), "unknown error") == 0);
 
     swec_encoder *enc = NULL;

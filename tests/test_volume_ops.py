@@ -152,7 +152,107 @@ def test_ec_shards_rebuild_prechecks_need_no_gpu(swec, oracle, tmp_path):
     assert not any(os.path.exists(base + ".ec%02d" % i) for i in range(5))
 
 
+def expected_record(dat, offset, size, version=3):
+    """What ReadEcShardNeedle's `bytes` holds: GetActualSize applied twice (ec_volume.go:395,414), taken from
+    the volume image zero-padded the way the last small row is."""
+    def actual(sz):
+        fixed = 16 + sz + 4 + (8 if version == 3 else 0)
+        return fixed + (8 - fixed % 8)
+    want = actual(actual(size))
+    padded = np.concatenate([dat, np.zeros(want + 16, dtype=np.uint8)])
+    return padded[offset:offset + want]
+
+
+def needle_volume(oracle, tmp_path, seed=17, with_vif=True):
+    dat, idx = synthetic_volume(seed=seed, needles=600)          # ≈12 MiB, two small rows: records straddle 1 MiB block borders
+    base, shards = lay_down_ec_volume(oracle, tmp_path, dat, idx)
+    if with_vif:
+        json.dump({"version": 3, "datFileSize": str(len(dat)), "ecShardConfig": {"dataShards": 10, "parityShards": 4}},
+                  open(base + ".vif", "w"))
+    live = [(k, o, s) for k, o, s in rn._entries(rn.sorted_ecx_from_idx(idx))]
+    return base, dat, live
+
+
+def test_read_ec_needles_all_shards_local_needs_no_gpu(swec, oracle, tmp_path):
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path)
+    assert len(live) > 50
+    open(base + ".ecj", "wb").write(live[3][0].to_bytes(8, "big"))       # deleted after sealing
+    ids = [k for k, _, _ in live] + [0xFFFFFFFFFF]
+    out = ec.ReadEcShardNeedles(base, ids, device=-1)                     # no recovery ⇒ no device needed
+    multi = 0
+    for (key, off, size), r in zip(live, out):
+        if key == live[3][0]:
+            assert r["status"] == "SWEC_ERR_DELETED" and r["size"] == -1
+            continue
+        assert r["status"] == "SWEC_OK" and r["offset"] == off * 8 and r["size"] == size and r["recovered_intervals"] == 0
+        want = expected_record(dat, off * 8, size)
+        assert r["n_bytes"] == len(want) and (r["bytes"] == want).all(), key
+        multi += (off * 8) // MIB != (off * 8 + len(want) - 1) // MIB
+    assert multi >= 1, "the volume should contain records that straddle block borders"
+    assert out[-1]["status"] == "SWEC_ERR_NOT_FOUND"
+    tiny = ec.ReadEcShardNeedles(base, [live[0][0]], device=-1, capacity=8)
+    assert tiny[0]["status"] == "SWEC_ERR_INVALID_ARG" and tiny[0]["n_bytes"] == len(expected_record(dat, 0, live[0][2]))
+
+
+def test_read_ec_needles_old_volume_without_vif(swec, oracle, tmp_path):
+    """No .vif ⇒ needle version 3 and shard size = shard file size - 1 (ec_volume.go:408-413)."""
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=23, with_vif=False)
+    out = ec.ReadEcShardNeedles(base, [k for k, _, _ in live[:40]], device=-1)
+    for (key, off, size), r in zip(live, out):
+        assert r["status"] == "SWEC_OK" and (r["bytes"] == expected_record(dat, off * 8, size)).all()
+
+
+def test_read_ec_needles_recovery_is_loud_without_gpu(swec, oracle, tmp_path):
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=29)
+    os.remove(base + ".ec00")
+    with pytest.raises(swec.SwecError) as e:
+        ec.ReadEcShardNeedles(base, [k for k, _, _ in live], device=-1)
+    assert e.value.name == "SWEC_ERR_NO_DEVICE"
+
+
 # ------------------------------------------------------------------------------------------ GPU
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lost", [(0,), (2, 5), (0, 1, 2, 3), (1, 9, 10, 13)])
+def test_read_ec_needles_degraded(cuda, swec, oracle, tmp_path, lost):
+    """Degraded reads: the shard files in `lost` are gone; every record is still returned byte-exactly, the
+    intervals that lived on lost shards being rebuilt by one batched ReconstructData on the GPU."""
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=41 + len(lost))
+    other = tmp_path / "disk2"
+    other.mkdir()
+    os.rename(base + ".ec06", str(other / "7.ec06"))                      # one healthy shard lives on another disk
+    for i in lost:
+        os.remove(base + ".ec%02d" % i)
+    before = swec.lib().swec_kernel_launches()
+    out = ec.ReadEcShardNeedles(base, [k for k, _, _ in live], additional_dirs=[str(other)])
+    recovered = 0
+    for (key, off, size), r in zip(live, out):
+        assert r["status"] == "SWEC_OK", (key, r["status"])
+        assert (r["bytes"] == expected_record(dat, off * 8, size)).all(), key
+        recovered += r["recovered_intervals"]
+    data_lost = [i for i in lost if i < 10]
+    assert (recovered > 0) == bool(data_lost)
+    launches = swec.lib().swec_kernel_launches() - before
+    assert launches <= 8 if data_lost else launches == 0, launches       # batched: not one launch per interval
+
+
+@pytest.mark.gpu
+def test_read_ec_needles_too_few_shards(cuda, swec, oracle, tmp_path):
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=47)
+    for i in (0, 1, 2, 3, 4):
+        os.remove(base + ".ec%02d" % i)
+    out = ec.ReadEcShardNeedles(base, [k for k, _, _ in live])
+    kinds = {r["status"] for r in out}
+    assert kinds == {"SWEC_OK", "SWEC_ERR_TOO_FEW_SHARDS"}               # records wholly on shards 5-9 still read
+    for (key, off, size), r in zip(live, out):
+        if r["status"] == "SWEC_OK":
+            assert r["recovered_intervals"] == 0 and (r["bytes"] == expected_record(dat, off * 8, size)).all()
+
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("volume", ["fixture", "synthetic"])
