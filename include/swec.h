@@ -214,6 +214,16 @@ typedef struct swec_needle_read {
 int swec_read_ec_needles(const char *data_base_file_name, const char *index_base_file_name,
                          const char *const *additional_dirs, int n_additional_dirs,
                          swec_needle_read *reads, int n_reads, int device);
+/* The same on a MOUNTED volume — the twin of the long-lived EcVolume (ec_volume.go:36-160): open once
+ * (ratio / needle version / datFileSize from .vif, shard files opened, .ecx loaded, .ecj re-read when it
+ * grows), read many times; the encoder behind the recoveries, its staging ring and its specialised kernels
+ * live as long as the handle.  Calls on one handle serialise.  swec_read_ec_needles = open + read + close. */
+typedef struct swec_ec_volume swec_ec_volume;
+int swec_ec_volume_open(const char *data_base_file_name, const char *index_base_file_name,
+                        const char *const *additional_dirs, int n_additional_dirs, int device,
+                        swec_ec_volume **out);
+int swec_ec_volume_read_needles(swec_ec_volume *vol, swec_needle_read *reads, int n_reads);
+void swec_ec_volume_close(swec_ec_volume *vol);
 
 /* ---- index files either side of the path (host only, no GPU) ---------------------------------- */
 /* WriteSortedFileFromIdx(base, ext): base.idx → base+ext (".ecx"), live entries sorted by needle id

@@ -45,12 +45,25 @@ def main():
             sample = ids[:400]
             l0, t0 = L.swec_kernel_launches(), time.perf_counter()
             for nid in sample:
-                ec.ReadEcShardNeedles(base, [nid])
+                ec.ReadEcShardNeedles(base, [nid], capacity=1 << 17)
             t_single, l_single = (time.perf_counter() - t0) / len(sample), (L.swec_kernel_launches() - l0) / len(sample)
+            vol = ec.EcVolume(base)
+            vol.ReadEcShardNeedles(ids[:8])
+            t0 = time.perf_counter()
+            out2 = vol.ReadEcShardNeedles(ids)
+            t_mounted_batch = time.perf_counter() - t0
+            assert all((a["bytes"] == b["bytes"]).all() for a, b in zip(out, out2))
+            t0 = time.perf_counter()
+            for nid in sample:
+                vol.ReadEcShardNeedles([nid], capacity=1 << 17)
+            t_mounted_single = (time.perf_counter() - t0) / len(sample)
+            vol.close()
             print(json.dumps({"volume_MiB": round(len(dat) / 2**20, 1), "needles": len(ids), "lost_shards": list(lost),
                               "recovered_intervals": sum(r["recovered_intervals"] for r in out),
                               "one_call_all_needles": {"needles_per_s": round(len(ids) / t_batch), "MBps": round(sum(r["n_bytes"] for r in out) / t_batch / 1e6, 1), "gpu_launches": int(l_batch)},
-                              "one_call_per_needle": {"needles_per_s": round(1 / t_single), "gpu_launches_per_needle": round(l_single, 2)}}),
+                              "one_call_per_needle": {"needles_per_s": round(1 / t_single), "gpu_launches_per_needle": round(l_single, 2)},
+                              "mounted_volume": {"all_needles_one_call_per_s": round(len(ids) / t_mounted_batch),
+                                                 "one_needle_per_call_per_s": round(1 / t_mounted_single)}}),
                   flush=True)
 
 

@@ -84,6 +84,9 @@ PROTOTYPES = {
                                          C.POINTER(C.c_int)]),
     "swec_ec_shards_to_volume": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "swec_read_ec_needles": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(NeedleRead), C.c_int, C.c_int]),
+    "swec_ec_volume_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "swec_ec_volume_read_needles": (C.c_int, [C.c_void_p, C.POINTER(NeedleRead), C.c_int]),
+    "swec_ec_volume_close": (None, [C.c_void_p]),
     "swec_write_sorted_file_from_idx": (C.c_int, [C.c_char_p, C.c_char_p]),
     "swec_rebuild_ecx_file": (C.c_int, [C.c_char_p]),
     "swec_write_idx_file_from_ec_index": (C.c_int, [C.c_char_p]),

@@ -22,6 +22,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -134,14 +136,6 @@ int64_t needle_actual_size(int64_t size, int version) {
     return fixed + (8 - fixed % 8);
 }
 
-struct FdCloser {
-    std::vector<int> fds;
-    ~FdCloser() {
-        for (int fd : fds)
-            if (fd >= 0) close(fd);
-    }
-};
-
 }  // namespace
 }  // namespace swec
 
@@ -252,33 +246,57 @@ int swec_ec_shards_to_volume(const char* data_base, const char* index_base, cons
     return SWEC_OK;
 }
 
-int swec_read_ec_needles(const char* data_base, const char* index_base, const char* const* additional_dirs,
-                         int n_additional_dirs, swec_needle_read* reads, int n_reads, int device) {
-    if (!data_base || (n_reads > 0 && !reads) || (n_additional_dirs > 0 && !additional_dirs))
-        return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+// ---- EcVolume: the mounted state the read path works from (ec_volume.go:36-160) ------------------
+
+}  // extern "C"
+
+struct swec_ec_volume {
+    std::mutex mu;
+    int k = 10, m = 4, version = 3, device = 0;
+    int64_t shard_dat_size = 0;
+    std::string index_base;
+    std::vector<int> shard_fd;  // total entries, -1 = not local
+    std::string ecx, ecj;
+    int64_t ecj_size_seen = -1;
+    swec_encoder* enc = nullptr;  // created on the first recovery, keeps its staging ring and kernels
+    ~swec_ec_volume() {
+        for (int fd : shard_fd)
+            if (fd >= 0) close(fd);
+        if (enc) swec_encoder_free(enc);
+    }
+};
+
+extern "C" {
+
+int swec_ec_volume_open(const char* data_base, const char* index_base, const char* const* additional_dirs,
+                        int n_additional_dirs, int device, swec_ec_volume** out) {
+    if (!out) return fail(SWEC_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!data_base || (n_additional_dirs > 0 && !additional_dirs)) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
     const std::string db(data_base);
     std::string ib(index_base && *index_base ? index_base : data_base);
     if (!is_file(ib + ".ecx")) ib = db;  // NewEcVolume falls back to the data directory (ec_volume.go:72-85)
+    std::unique_ptr<swec_ec_volume> v(new (std::nothrow) swec_ec_volume());
+    if (!v) return fail(SWEC_ERR_NOMEM, "out of memory");
+    v->device = device;
+    v->index_base = ib;
 
-    // ---- what NewEcVolume loads: ratio, needle version and datFileSize from .vif (ec_volume.go:114-154)
-    int k, m;
-    ratio_from_vif(db, &k, &m);
-    const int total = k + m;
-    int version = 3;
+    // what NewEcVolume loads: ratio, needle version and datFileSize from .vif (ec_volume.go:114-154)
+    ratio_from_vif(db, &v->k, &v->m);
+    const int total = v->k + v->m;
     int64_t dat_file_size = 0;
     {
         std::string vif;
         if (slurp(db + ".vif", &vif) || slurp(ib + ".vif", &vif)) {
-            int64_t v = 0;
-            if (vif_number(vif, "version", &v) && v > 0) version = int(v);
-            if (vif_number(vif, "datFileSize", &v)) dat_file_size = v;
+            int64_t x = 0;
+            if (vif_number(vif, "version", &x) && x > 0) v->version = int(x);
+            if (vif_number(vif, "datFileSize", &x)) dat_file_size = x;
         }
     }
-    // ---- local shards (data_base's directory, then the other disks)
+    // local shards: data_base's directory, then the other disks
     std::string base_copy(db);
     const std::string base_name = basename(&base_copy[0]);
-    FdCloser fds;
-    std::vector<int> shard_fd(size_t(total), -1);
+    v->shard_fd.assign(size_t(total), -1);
     int64_t ecd_file_size = -1;
     int nlocal = 0;
     for (int i = 0; i < total; i++) {
@@ -295,9 +313,8 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
         }
         if (path.empty()) continue;
         const int fd = open(path.c_str(), O_RDONLY);
-        if (fd < 0) continue;  // unreadable = not local; the interval is recovered from the others
-        fds.fds.push_back(fd);
-        shard_fd[size_t(i)] = fd;
+        if (fd < 0) continue;  // unreadable = not local; its intervals are recovered from the others
+        v->shard_fd[size_t(i)] = fd;
         nlocal++;
         if (ecd_file_size < 0) {
             struct stat st;
@@ -307,18 +324,35 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
     if (nlocal == 0) return fail(SWEC_ERR_TOO_FEW_SHARDS, "ec shard " + db + " not found");
     // LocateEcShardNeedleInterval: .vif's datFileSize is authoritative; old volumes fall back to the
     // shard file size minus one (ec_volume.go:399-417)
-    const int64_t shard_dat_size = dat_file_size > 0 ? dat_file_size / k : ecd_file_size - 1;
+    v->shard_dat_size = dat_file_size > 0 ? dat_file_size / v->k : ecd_file_size - 1;
+    if (!slurp(ib + ".ecx", &v->ecx)) return fail(SWEC_ERR_IO, "cannot open ec volume index " + ib + ".ecx: " + strerror(errno));
+    *out = v.release();
+    return SWEC_OK;
+}
+
+void swec_ec_volume_close(swec_ec_volume* v) { delete v; }
+
+int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int n_reads) {
+    if (!v || (n_reads > 0 && !reads)) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    const int k = v->k, total = v->k + v->m, version = v->version;
     const int64_t large = int64_t(1) << 30, small = int64_t(1) << 20;
 
-    // ---- the sealed index plus the deletion journal (FindNeedleFromEcx, ec_volume.go:419-429)
-    std::string ecx, ecj;
-    if (!slurp(ib + ".ecx", &ecx)) return fail(SWEC_ERR_IO, "cannot open ec volume index " + ib + ".ecx: " + strerror(errno));
-    slurp(ib + ".ecj", &ecj);
-    const uint8_t* ex = reinterpret_cast<const uint8_t*>(ecx.data());
-    const int64_t entries = int64_t(ecx.size()) / 16;
+    // the deletion journal grows while the volume is mounted (DeleteNeedleFromEcx appends to .ecj): pick up
+    // new entries when the file size moved — the reference keeps the same set in memory (ec_volume.go:351-384)
+    {
+        struct stat st;
+        const int64_t now = stat((v->index_base + ".ecj").c_str(), &st) == 0 ? int64_t(st.st_size) : 0;
+        if (now != v->ecj_size_seen) {
+            if (now == 0 || !slurp(v->index_base + ".ecj", &v->ecj)) v->ecj.clear();
+            v->ecj_size_seen = now;
+        }
+    }
+    const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
+    const int64_t entries = int64_t(v->ecx.size()) / 16;
     auto journalled = [&](uint64_t id) {
-        for (size_t off = 0; off + 8 <= ecj.size(); off += 8)
-            if (be64(reinterpret_cast<const uint8_t*>(ecj.data()) + off) == id) return true;
+        for (size_t off = 0; off + 8 <= v->ecj.size(); off += 8)
+            if (be64(reinterpret_cast<const uint8_t*>(v->ecj.data()) + off) == id) return true;
         return false;
     };
 
@@ -356,7 +390,7 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
         }
         const int64_t offset = int64_t(be32(ex + found * 16 + 8)) * 8;  // Offset.ToActualOffset (offset_4bytes.go)
         int32_t size = int32_t(be32(ex + found * 16 + 12));
-        if (journalled(rd.needle_id)) size = -1;  // TombstoneFileSize
+        if (journalled(rd.needle_id)) size = -1;  // TombstoneFileSize (FindNeedleFromEcx, ec_volume.go:419-429)
         rd.offset = offset;
         rd.size = size;
         if (size < 0) {  // Size.IsDeleted
@@ -373,7 +407,7 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
             continue;
         }
         swec_interval ivs[64];
-        const int niv = swec_locate_data(large, small, shard_dat_size, offset, want, k, ivs, 64);
+        const int niv = swec_locate_data(large, small, v->shard_dat_size, offset, want, k, ivs, 64);
         if (niv < 0) {
             rd.status = niv;
             continue;
@@ -385,8 +419,8 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
             swec_interval_to_shard(&ivs[j], large, small, k, &sid, &soff);
             const size_t len = size_t(ivs[j].size);
             bool ok = false;
-            if (shard_fd[size_t(sid)] >= 0) {  // readLocalEcShardInterval (store_ec.go:407-422): all or nothing
-                const ssize_t got = pread(shard_fd[size_t(sid)], rd.buf + pos, len, off_t(soff));
+            if (v->shard_fd[size_t(sid)] >= 0) {  // readLocalEcShardInterval (store_ec.go:407-422): all or nothing
+                const ssize_t got = pread(v->shard_fd[size_t(sid)], rd.buf + pos, len, off_t(soff));
                 ok = got == ssize_t(len);
             }
             if (!ok) {  // recoverOneRemoteEcShardInterval, with "remote" = every other local shard file
@@ -396,13 +430,12 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
                 rc.len = len;
                 rc.shard = sid;
                 rc.bufs.resize(size_t(total));
-                rc.ptrs.assign(size_t(total), nullptr);
                 rc.present.assign(size_t(total), 0);
                 int have = 0;
                 for (int i = 0; i < total; i++) {
-                    if (i == sid || shard_fd[size_t(i)] < 0) continue;
+                    if (i == sid || v->shard_fd[size_t(i)] < 0) continue;
                     rc.bufs[size_t(i)].resize(len);
-                    if (pread(shard_fd[size_t(i)], rc.bufs[size_t(i)].data(), len, off_t(soff)) == ssize_t(len)) {
+                    if (pread(v->shard_fd[size_t(i)], rc.bufs[size_t(i)].data(), len, off_t(soff)) == ssize_t(len)) {
                         rc.present[size_t(i)] = 1;
                         have++;
                     } else {
@@ -417,7 +450,6 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
                 }
                 for (int i = 0; i < k; i++)  // ReconstructData fills every missing DATA shard
                     if (!rc.present[size_t(i)]) rc.bufs[size_t(i)].resize(len);
-                for (int i = 0; i < total; i++) rc.ptrs[size_t(i)] = rc.bufs[size_t(i)].empty() ? nullptr : rc.bufs[size_t(i)].data();
                 recs.push_back(std::move(rc));
                 rd.n_recovered_intervals++;
             }
@@ -428,20 +460,21 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
 
     // ---- pass 2: every interval that needs the arithmetic, in ONE batched ReconstructData on the GPU
     if (!recs.empty()) {
-        swec_encoder* enc = nullptr;
-        int rc = swec_encoder_new(k, m, device, &enc);
-        if (rc) return rc;
-        std::unique_ptr<swec_encoder, void (*)(swec_encoder*)> guard(enc, swec_encoder_free);
+        if (!v->enc) {
+            const int rc = swec_encoder_new(v->k, v->m, v->device, &v->enc);
+            if (rc) return rc;
+        }
         std::vector<swec_reconstruct_item> items(recs.size());
         for (size_t j = 0; j < recs.size(); j++) {
-            // the moves above kept the heap blocks, but rebuild the pointer table to be safe
-            for (int i = 0; i < total; i++) recs[j].ptrs[size_t(i)] = recs[j].bufs[size_t(i)].empty() ? nullptr : recs[j].bufs[size_t(i)].data();
+            recs[j].ptrs.assign(size_t(total), nullptr);
+            for (int i = 0; i < total; i++)
+                if (!recs[j].bufs[size_t(i)].empty()) recs[j].ptrs[size_t(i)] = recs[j].bufs[size_t(i)].data();
             items[j].shards = recs[j].ptrs.data();
             items[j].present = recs[j].present.data();
             items[j].shard_len = recs[j].len;
             items[j].data_only = 1;
         }
-        rc = swec_reconstruct_batch(enc, items.data(), int(items.size()));
+        const int rc = swec_reconstruct_batch(v->enc, items.data(), int(items.size()));
         if (rc) return rc;
         for (const Recover& rcv : recs) {
             swec_needle_read& rd = reads[rcv.read_idx];
@@ -450,6 +483,17 @@ int swec_read_ec_needles(const char* data_base, const char* index_base, const ch
         }
     }
     return SWEC_OK;
+}
+
+int swec_read_ec_needles(const char* data_base, const char* index_base, const char* const* additional_dirs,
+                         int n_additional_dirs, swec_needle_read* reads, int n_reads, int device) {
+    if (n_reads > 0 && !reads) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    swec_ec_volume* v = nullptr;
+    int rc = swec_ec_volume_open(data_base, index_base, additional_dirs, n_additional_dirs, device, &v);
+    if (rc) return rc;
+    rc = swec_ec_volume_read_needles(v, reads, n_reads);
+    swec_ec_volume_close(v);
+    return rc;
 }
 
 }  // extern "C"

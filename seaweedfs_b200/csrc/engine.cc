@@ -517,7 +517,12 @@ static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std
     std::lock_guard<std::mutex> lock(e->mu);
     int rc = e->ensure_device();
     if (rc) return rc;
-    const size_t chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
+    // size the ring for THIS batch (a lone degraded read must not pin 3 x 18 x 16 MiB): everything packed
+    // back to back, capped by the configured chunk; ensure_slots only ever grows an existing ring
+    const size_t max_chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
+    size_t packed = 0;
+    for (const Segment& sg : segs) packed += (sg.len + 15) & ~size_t(15);
+    const size_t chunk = std::min(max_chunk, (packed + 65535) & ~size_t(65535));
     if ((rc = e->ensure_slots(chunk))) return rc;
     const size_t stride = e->slot_chunk;
     DrainSlotsOnExit drain{e};

@@ -323,22 +323,56 @@ def volume_ec_shards_to_volume(data_base_file_name: str, index_base_file_name: s
     return int(size.value)
 
 
+def _needle_reads(needle_ids, capacity):
+    reads = (NeedleRead * len(needle_ids))()
+    arena = np.empty(max(1, len(needle_ids)) * capacity, dtype=np.uint8)      # untouched pages cost nothing
+    for j, (r, nid) in enumerate(zip(reads, needle_ids)):
+        r.needle_id, r.buf, r.capacity = nid, arena.ctypes.data + j * capacity, capacity
+    return reads, arena
+
+
+def _needle_results(reads, arena, capacity):
+    return [{"id": r.needle_id, "status": STATUS.get(r.status, str(r.status)), "offset": r.offset, "size": r.size,
+             "bytes": arena[j * capacity: j * capacity + r.n_bytes].copy() if r.status == 0 else None,
+             "n_bytes": r.n_bytes, "recovered_intervals": r.n_recovered_intervals} for j, r in enumerate(reads)]
+
+
+class EcVolume:
+    """A mounted EC volume (erasure_coding.EcVolume, ec_volume.go:36-160) for the read path: shard files open,
+    .ecx loaded, the encoder behind degraded reads kept warm.  ReadEcShardNeedles = Store.ReadEcShardNeedle
+    (store_ec.go:252-355) for many needles in one call."""
+
+    def __init__(self, data_base_file_name: str, index_base_file_name: str | None = None,
+                 additional_dirs: list[str] | None = None, device: int = 0):
+        arr, n = _dirs(additional_dirs)
+        h = C.c_void_p()
+        check(lib().swec_ec_volume_open(data_base_file_name.encode(), (index_base_file_name or "").encode(), arr, n,
+                                        device, C.byref(h)))
+        self._h = h
+
+    def read_needles(self, needle_ids: list[int], capacity: int = 1 << 20):
+        reads, arena = _needle_reads(needle_ids, capacity)
+        check(lib().swec_ec_volume_read_needles(self._h, reads, len(needle_ids)))
+        return _needle_results(reads, arena, capacity)
+
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h and callable(lib):
+            lib().swec_ec_volume_close(h)
+
+    __del__ = close
+    ReadEcShardNeedles = read_needles
+
+
 def read_ec_shard_needles(data_base_file_name: str, needle_ids: list[int], index_base_file_name: str | None = None,
                           additional_dirs: list[str] | None = None, device: int = 0, capacity: int = 1 << 20):
-    """Store.ReadEcShardNeedle for many needles at once (store_ec.go:252-355): returns one dict per id with
-    status name, offset, size, the raw record bytes and how many intervals had to be reconstructed."""
+    """One-shot form: mount, read, unmount.  Returns one dict per id with status name, offset, size, the raw
+    record bytes and how many intervals had to be reconstructed."""
     arr, n = _dirs(additional_dirs)
-    reads = (NeedleRead * len(needle_ids))()
-    bufs = []
-    for r, nid in zip(reads, needle_ids):
-        b = np.zeros(capacity, dtype=np.uint8)
-        bufs.append(b)
-        r.needle_id, r.buf, r.capacity = nid, b.ctypes.data, capacity
+    reads, arena = _needle_reads(needle_ids, capacity)
     check(lib().swec_read_ec_needles(data_base_file_name.encode(), (index_base_file_name or "").encode(), arr, n,
                                      reads, len(needle_ids), device))
-    return [{"id": r.needle_id, "status": STATUS.get(r.status, str(r.status)), "offset": r.offset, "size": r.size,
-             "bytes": b[: r.n_bytes].copy() if r.status == 0 else None, "n_bytes": r.n_bytes,
-             "recovered_intervals": r.n_recovered_intervals} for r, b in zip(reads, bufs)]
+    return _needle_results(reads, arena, capacity)
 
 
 ReadEcShardNeedles = read_ec_shard_needles

@@ -195,6 +195,26 @@ def test_read_ec_needles_all_shards_local_needs_no_gpu(swec, oracle, tmp_path):
     assert tiny[0]["status"] == "SWEC_ERR_INVALID_ARG" and tiny[0]["n_bytes"] == len(expected_record(dat, 0, live[0][2]))
 
 
+def test_mounted_ec_volume_sees_journal_growth(swec, oracle, tmp_path):
+    """An EcVolume handle stays open across reads; a needle deleted meanwhile (DeleteNeedleFromEcx appends its
+    id to .ecj) reads as deleted on the next call, like the reference's in-memory deleted set."""
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=19)
+    vol = ec.EcVolume(base, device=-1)
+    ids = [k for k, _, _ in live[:20]]
+    first = vol.ReadEcShardNeedles(ids)
+    assert all(r["status"] == "SWEC_OK" for r in first)
+    with open(base + ".ecj", "ab") as f:
+        f.write(ids[5].to_bytes(8, "big"))
+    second = vol.ReadEcShardNeedles(ids)
+    assert [r["status"] for r in second] == ["SWEC_ERR_DELETED" if i == 5 else "SWEC_OK" for i in range(20)]
+    assert all((a["bytes"] == b["bytes"]).all() for i, (a, b) in enumerate(zip(first, second)) if i != 5)
+    vol.close()
+    with pytest.raises(swec.SwecError) as e:
+        ec.EcVolume(str(tmp_path / "nothing-here"), device=-1)
+    assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS"
+
+
 def test_read_ec_needles_old_volume_without_vif(swec, oracle, tmp_path):
     """No .vif ⇒ needle version 3 and shard size = shard file size - 1 (ec_volume.go:408-413)."""
     ec = swec.erasure_coding
@@ -238,6 +258,29 @@ def test_read_ec_needles_degraded(cuda, swec, oracle, tmp_path, lost):
     assert (recovered > 0) == bool(data_lost)
     launches = swec.lib().swec_kernel_launches() - before
     assert launches <= 8 if data_lost else launches == 0, launches       # batched: not one launch per interval
+
+
+@pytest.mark.gpu
+def test_mounted_ec_volume_degraded_reads_reuse_the_encoder(cuda, swec, oracle, tmp_path):
+    """One needle per call on a mounted volume (the shape of today's read path): the handle's encoder, staging
+    ring and kernels are created once, so a lone degraded read costs one small launch, not a re-initialisation."""
+    import time
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=53)
+    for i in (0, 1, 2, 3):
+        os.remove(base + ".ec%02d" % i)
+    vol = ec.EcVolume(base)
+    vol.ReadEcShardNeedles([live[0][0]], capacity=1 << 16)
+    t0, n, recovered = time.perf_counter(), 0, 0
+    for key, off, size in live[:200]:
+        r = vol.ReadEcShardNeedles([key], capacity=1 << 17)[0]
+        assert r["status"] == "SWEC_OK" and (r["bytes"] == expected_record(dat, off * 8, size)).all()
+        recovered += r["recovered_intervals"]
+        n += 1
+    per_call = (time.perf_counter() - t0) / n
+    assert recovered > 20
+    assert per_call < 0.02, f"{per_call * 1e3:.1f} ms per single-needle read: the encoder is not being reused"
+    vol.close()
 
 
 @pytest.mark.gpu
