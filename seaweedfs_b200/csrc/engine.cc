@@ -544,16 +544,14 @@ static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std
         StagingSlot& sl = e->slots[si];
         const uint8_t* din[SWEC_MAX_INPUTS];
         uint8_t* dout[SWEC_MAX_SHARDS];
-        for (int i = 0; i < K; i++) {
-            din[i] = sl.dev + size_t(i) * stride;
-            SWEC_CUDA(cudaMemcpyAsync(sl.dev + size_t(i) * stride, sl.host + size_t(i) * stride, fill,
-                                      cudaMemcpyHostToDevice, sl.stream));
-        }
+        for (int i = 0; i < K; i++) din[i] = sl.dev + size_t(i) * stride;
+        // the K input streams sit at pitch `stride` in both buffers: one strided DMA instead of K small ones
+        SWEC_CUDA(cudaMemcpy2DAsync(sl.dev, stride, sl.host, stride, fill, size_t(K), cudaMemcpyHostToDevice, sl.stream));
         for (int r = 0; r < R; r++) dout[r] = sl.dev + size_t(K + r) * stride;
         const int rc2 = e->apply(rows, din, dout, fill, Layout{}, sl.stream);
         if (rc2) return rc2;
-        for (int r = 0; r < R; r++)
-            SWEC_CUDA(cudaMemcpyAsync(sl.host + size_t(K + r) * stride, dout[r], fill, cudaMemcpyDeviceToHost, sl.stream));
+        SWEC_CUDA(cudaMemcpy2DAsync(sl.host + size_t(K) * stride, stride, dout[0], stride, fill, size_t(R),
+                                    cudaMemcpyDeviceToHost, sl.stream));
         SWEC_CUDA(cudaEventRecord(sl.done, sl.stream));
         sl.busy = true;
         fill = 0;
