@@ -16,6 +16,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+CAP = 1 << 17     # per-needle buffer; small on purpose: 1 MiB strides make every first touch a 2 MiB THP fault
+
+
 def main():
     import seaweedfs_b200
     from oracle import pyoracle as po
@@ -36,26 +39,26 @@ def main():
         for lost in ((), (0, 1, 2, 3)):
             for i in lost:
                 os.remove(base + ".ec%02d" % i)
-            ec.ReadEcShardNeedles(base, ids[:8])                         # warm-up (tables, staging ring)
+            ec.ReadEcShardNeedles(base, ids[:8], capacity=CAP)           # warm-up (tables, staging ring)
             l0, t0 = L.swec_kernel_launches(), time.perf_counter()
-            out = ec.ReadEcShardNeedles(base, ids)
+            out = ec.ReadEcShardNeedles(base, ids, capacity=CAP)
             t_batch, l_batch = time.perf_counter() - t0, L.swec_kernel_launches() - l0
             for (key, off, size), r in zip(live, out):
                 assert r["status"] == "SWEC_OK" and (r["bytes"] == expected_record(dat, off * 8, size)).all()
             sample = ids[:400]
             l0, t0 = L.swec_kernel_launches(), time.perf_counter()
             for nid in sample:
-                ec.ReadEcShardNeedles(base, [nid], capacity=1 << 17)
+                ec.ReadEcShardNeedles(base, [nid], capacity=CAP)
             t_single, l_single = (time.perf_counter() - t0) / len(sample), (L.swec_kernel_launches() - l0) / len(sample)
             vol = ec.EcVolume(base)
-            vol.ReadEcShardNeedles(ids[:8])
+            vol.ReadEcShardNeedles(ids[:8], capacity=CAP)
             t0 = time.perf_counter()
-            out2 = vol.ReadEcShardNeedles(ids)
+            out2 = vol.ReadEcShardNeedles(ids, capacity=CAP)
             t_mounted_batch = time.perf_counter() - t0
             assert all((a["bytes"] == b["bytes"]).all() for a, b in zip(out, out2))
             t0 = time.perf_counter()
             for nid in sample:
-                vol.ReadEcShardNeedles([nid], capacity=1 << 17)
+                vol.ReadEcShardNeedles([nid], capacity=CAP)
             t_mounted_single = (time.perf_counter() - t0) / len(sample)
             vol.close()
             print(json.dumps({"volume_MiB": round(len(dat) / 2**20, 1), "needles": len(ids), "lost_shards": list(lost),
