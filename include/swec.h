@@ -223,6 +223,9 @@ int swec_ec_volume_open(const char *data_base_file_name, const char *index_base_
                         const char *const *additional_dirs, int n_additional_dirs, int device,
                         swec_ec_volume **out);
 int swec_ec_volume_read_needles(swec_ec_volume *vol, swec_needle_read *reads, int n_reads);
+/* EcVolume.DeleteNeedleFromEcx (ec_volume_delete.go:28-93): append the id to the .ecj journal (fsync'ed
+ * before it becomes visible to reads); unknown, tombstoned or already journalled ids are not errors.  */
+int swec_ec_volume_delete_needle(swec_ec_volume *vol, uint64_t needle_id);
 void swec_ec_volume_close(swec_ec_volume *vol);
 
 /* ---- index files either side of the path (host only, no GPU) ---------------------------------- */

@@ -485,6 +485,64 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
     return SWEC_OK;
 }
 
+// DeleteNeedleFromEcx (ec_volume_delete.go:28-93): .ecx stays sealed; a runtime delete appends the id to the
+// .ecj journal (the durable commit point: written, fsync'ed, truncated back on failure) and only then becomes
+// visible to reads.  Unknown ids and ids that are already tombstoned / journalled are not errors.
+int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
+    if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");
+    std::lock_guard<std::mutex> lock(v->mu);
+    const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
+    int64_t lo = 0, hi = int64_t(v->ecx.size()) / 16, found = -1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) / 2;
+        const uint64_t key = be64(ex + mid * 16);
+        if (key == needle_id) {
+            found = mid;
+            break;
+        }
+        if (key < needle_id) lo = mid + 1;
+        else hi = mid;
+    }
+    if (found < 0) return SWEC_OK;                                   // already gone
+    if (int32_t(be32(ex + found * 16 + 12)) < 0) return SWEC_OK;     // folded into .ecx by an earlier rebuild
+    const std::string path = v->index_base + ".ecj";
+    const int fd = open(path.c_str(), O_RDWR | O_CREAT, 0644);
+    if (fd < 0) return fail(SWEC_ERR_IO, "cannot open ec volume journal " + path + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        const int e = errno;
+        close(fd);
+        return fail(SWEC_ERR_IO, "stat ecj: " + std::string(strerror(e)));
+    }
+    std::string cur(size_t(st.st_size), '\0');
+    if (st.st_size > 0 && pread(fd, &cur[0], cur.size(), 0) != ssize_t(cur.size())) {
+        const int e = errno;
+        close(fd);
+        return fail(SWEC_ERR_IO, "read ecj: " + std::string(strerror(e)));
+    }
+    for (size_t off = 0; off + 8 <= cur.size(); off += 8)
+        if (be64(reinterpret_cast<const uint8_t*>(cur.data()) + off) == needle_id) {  // idempotent
+            close(fd);
+            v->ecj = cur;
+            v->ecj_size_seen = st.st_size;
+            return SWEC_OK;
+        }
+    uint8_t b[8];
+    for (int i = 0; i < 8; i++) b[i] = uint8_t(needle_id >> (8 * (7 - i)));
+    const bool ok = pwrite(fd, b, 8, st.st_size) == 8 && fsync(fd) == 0;
+    const int e = errno;
+    if (!ok) {
+        if (ftruncate(fd, st.st_size) != 0) {}  // keep journal and in-memory state from drifting
+        close(fd);
+        return fail(SWEC_ERR_IO, "write ecj: " + std::string(strerror(e)));
+    }
+    close(fd);
+    cur.append(reinterpret_cast<const char*>(b), 8);
+    v->ecj = cur;
+    v->ecj_size_seen = st.st_size + 8;
+    return SWEC_OK;
+}
+
 int swec_read_ec_needles(const char* data_base, const char* index_base, const char* const* additional_dirs,
                          int n_additional_dirs, swec_needle_read* reads, int n_reads, int device) {
     if (n_reads > 0 && !reads) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");

@@ -355,6 +355,12 @@ class EcVolume:
         check(lib().swec_ec_volume_read_needles(self._h, reads, len(needle_ids)))
         return _needle_results(reads, arena, capacity)
 
+    def delete_needle(self, needle_id: int) -> None:
+        """DeleteNeedleFromEcx (ec_volume_delete.go:28-93)"""
+        check(lib().swec_ec_volume_delete_needle(self._h, needle_id))
+
+    DeleteNeedleFromEcx = delete_needle
+
     def close(self) -> None:
         h, self._h = getattr(self, "_h", None), None
         if h and callable(lib):

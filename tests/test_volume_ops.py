@@ -209,6 +209,21 @@ def test_mounted_ec_volume_sees_journal_growth(swec, oracle, tmp_path):
     second = vol.ReadEcShardNeedles(ids)
     assert [r["status"] for r in second] == ["SWEC_ERR_DELETED" if i == 5 else "SWEC_OK" for i in range(20)]
     assert all((a["bytes"] == b["bytes"]).all() for i, (a, b) in enumerate(zip(first, second)) if i != 5)
+    # DeleteNeedleFromEcx: journal append, idempotent, unknown ids ignored; then the fold sees all of it
+    vol.DeleteNeedleFromEcx(ids[7])
+    vol.DeleteNeedleFromEcx(ids[7])
+    vol.DeleteNeedleFromEcx(ids[5])                                      # journalled by someone else already
+    vol.DeleteNeedleFromEcx(0xABCDEF0123)                                # not in the volume
+    assert open(base + ".ecj", "rb").read() == ids[5].to_bytes(8, "big") + ids[7].to_bytes(8, "big")
+    third = vol.ReadEcShardNeedles(ids)
+    assert [i for i, r in enumerate(third) if r["status"] == "SWEC_ERR_DELETED"] == [5, 7]
+    vol.close()
+    ec.RebuildEcxFile(base)
+    assert sum(1 for _, _, sz in rn._entries(open(base + ".ecx", "rb").read()) if sz < 0) == 2
+    vol = ec.EcVolume(base, device=-1)                                   # tombstones in .ecx read as deleted too
+    assert [r["status"] for r in vol.ReadEcShardNeedles([ids[5], ids[6]])] == ["SWEC_ERR_DELETED", "SWEC_OK"]
+    vol.DeleteNeedleFromEcx(ids[5])                                      # already folded: nothing journalled
+    assert not os.path.exists(base + ".ecj") or os.path.getsize(base + ".ecj") == 0
     vol.close()
     with pytest.raises(swec.SwecError) as e:
         ec.EcVolume(str(tmp_path / "nothing-here"), device=-1)
