@@ -230,6 +230,26 @@ def test_mounted_ec_volume_sees_journal_growth(swec, oracle, tmp_path):
     assert e.value.name == "SWEC_ERR_TOO_FEW_SHARDS"
 
 
+def test_ecx_search_on_reference_fixture_389(swec, tmp_path):
+    """TestPositioning (ec_volume_test.go:14-58): SearchNeedleFromSortedIndex on the reference's 389.ecx (485,098
+    entries) finds the needles of its table at the listed offsets and sizes.  The fixture has no shard files, so
+    the reads themselves stop at "too few shards" — offset and size are reported all the same."""
+    fixture = os.path.join(ROOT, "oracle", "_ref", "389.ecx")
+    if not os.path.exists(fixture):
+        pytest.skip("oracle/_ref/389.ecx not shipped")
+    ec = swec.erasure_coding
+    base = str(tmp_path / "389")
+    os.symlink(fixture, base + ".ecx")
+    open(base + ".ec00", "wb").write(b"\x03" + b"\x00" * 7)           # a mounted volume needs one local shard
+    table = [(0x0F0EDB92, 31300679656, 1167), (0x0EF7D7F8, 11513014944, 66044)]
+    out = ec.ReadEcShardNeedles(base, [t[0] for t in table] + [0x0F087622, 1], device=-1)
+    for (nid, offset, size), r in zip(table, out):
+        assert (r["offset"], r["size"]) == (offset, size), hex(nid)
+        assert r["status"] == "SWEC_ERR_TOO_FEW_SHARDS"
+    assert out[2]["status"] == "SWEC_ERR_TOO_FEW_SHARDS" and out[2]["offset"] > 0      # found, like the Go test asserts
+    assert out[3]["status"] == "SWEC_ERR_NOT_FOUND"
+
+
 def test_read_ec_needles_old_volume_without_vif(swec, oracle, tmp_path):
     """No .vif ⇒ needle version 3 and shard size = shard file size - 1 (ec_volume.go:408-413)."""
     ec = swec.erasure_coding
