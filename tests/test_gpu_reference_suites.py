@@ -197,3 +197,17 @@ def test_parity_shard_recovery(cuda, swec, oracle, parity_shard):
     enc.Reconstruct(bufs)
     assert bufs[parity_shard] is not None and (bufs[parity_shard] == full[parity_shard]).all()
     enc.close()
+
+
+# ---- disk_location_ec_realworld_test.go ------------------------------------------------------------
+
+@pytest.mark.parametrize("dat_size", [1, 1024, 10 * 1024, 1 << 20, (1 << 20) + 1, 9 * (1 << 20) + 900 * 1024,
+                                      10 * (1 << 20) + 100 * 1024])
+def test_calculate_expected_shard_size_with_real_encoding(cuda, swec, oracle, tmp_path, dat_size):
+    """TestCalculateExpectedShardSizeEdgeCases (disk_location_ec_realworld_test.go:131-200): WriteEcFiles on
+    byte(i % 256) data, every shard file has the size calculateExpectedShardSize predicts."""
+    ec = swec.erasure_coding
+    dat = (np.arange(dat_size, dtype=np.int64) % 256).astype(np.uint8)
+    base, shards = encode_files(ec, oracle, tmp_path, dat, "edge", large=1 << 30, small=1 << 20, buffer=256 * 1024)
+    want = ec.expected_shard_size(dat_size)
+    assert all(os.path.getsize(base + ec.ToExt(i)) == want for i in range(14))

@@ -1,0 +1,121 @@
+"""Table-driven tests of the reference that need no GPU, re-run against libswec's host-side entry points (and
+the oracle): the expected-shard-size table and the .ecx / .ecj / .idx decode-side cases.
+
+  TestCalculateExpectedShardSize              weed/storage/disk_location_ec_shard_size_test.go:7-143
+  TestHasLiveNeedles_*, TestWriteIdxFileFromEcIndex_*, TestDecodeWithNonEmptyEcj_*, TestDecodeWithEmptyEcj,
+  TestDecodeWithNoEcjFile                     weed/storage/erasure_coding/ec_decoder_test.go:13-390
+"""
+import os
+
+import pytest
+
+from oracle import rs_numpy as rn
+
+GB, MB = 1 << 30, 1 << 20
+LARGE_BATCH, SMALL_BATCH = 10 * GB, 10 * MB
+
+SHARD_SIZE_TABLE = [                       # (name, datFileSize, expectedShardSize) — the reference's table, verbatim
+    ("0 bytes (empty file)", 0, 0),
+    ("Exact 10GB (1 large batch)", LARGE_BATCH, GB),
+    ("Exact 20GB (2 large batches)", 2 * LARGE_BATCH, 2 * GB),
+    ("Just under large batch (10GB - 1 byte)", LARGE_BATCH - 1, 1024 * MB),
+    ("Just over large batch (10GB + 1 byte)", LARGE_BATCH + 1, GB + MB),
+    ("Exact 10MB (1 small batch)", SMALL_BATCH, MB),
+    ("Exact 20MB (2 small batches)", 2 * SMALL_BATCH, 2 * MB),
+    ("Just under small batch (10MB - 1 byte)", SMALL_BATCH - 1, MB),
+    ("Just over small batch (10MB + 1 byte)", SMALL_BATCH + 1, 2 * MB),
+    ("10GB + 1MB", LARGE_BATCH + 1 * MB, GB + MB),
+    ("10GB + 5MB", LARGE_BATCH + 5 * MB, GB + MB),
+    ("10GB + 15MB", LARGE_BATCH + 15 * MB, GB + 2 * MB),
+    ("11GB (1 large batch + 103 small blocks)", 11 * GB, GB + 103 * MB),
+    ("5MB (requires 1 small block per shard)", 5 * MB, MB),
+    ("1KB (minimum size)", 1024, MB),
+    ("10.5GB (mixed)", 10 * GB + 512 * MB, GB + 52 * MB),
+]
+
+
+@pytest.mark.parametrize("name,dat_size,want", SHARD_SIZE_TABLE, ids=[t[0] for t in SHARD_SIZE_TABLE])
+def test_calculate_expected_shard_size(swec, oracle, name, dat_size, want):
+    assert swec.erasure_coding.expected_shard_size(dat_size) == want
+    assert oracle.expected_shard_size(dat_size) == want
+
+
+def entry(key, actual_offset, size):
+    """makeNeedleMapEntry(key, types.ToOffset(actual_offset), size)"""
+    return rn._entry(key, actual_offset // 8, size)
+
+
+def sizes(raw):
+    return [(k, s) for k, _, s in rn._entries(raw)]
+
+
+def test_has_live_needles(swec, tmp_path):
+    ec = swec.erasure_coding
+    base = str(tmp_path / "foo_1")
+    open(base + ".ecx", "wb").write(entry(1, 0, rn.TOMBSTONE))
+    assert ec.HasLiveNeedles(base) is False                              # _AllDeletedIsFalse
+    open(base + ".ecx", "wb").write(entry(1, 0, 1))
+    assert ec.HasLiveNeedles(base) is True                               # _WithLiveEntryIsTrue
+    open(base + ".ecx", "wb").write(b"")
+    assert ec.HasLiveNeedles(base) is False                              # _EmptyFileIsFalse
+
+
+def test_write_idx_file_from_ec_index_preserves_deleted_needles(swec, tmp_path):
+    ec = swec.erasure_coding
+    base = str(tmp_path / "foo_1")
+    ecx = entry(1, 64, 100) + entry(2, 128, rn.TOMBSTONE)
+    open(base + ".ecx", "wb").write(ecx)
+    ec.WriteIdxFileFromEcIndex(base)
+    idx = open(base + ".idx", "rb").read()
+    assert idx == ecx and sizes(idx)[1][1] < 0
+
+
+def test_write_idx_file_from_ec_index_processes_ecj_journal(swec, tmp_path):
+    ec = swec.erasure_coding
+    base = str(tmp_path / "foo_1")
+    open(base + ".ecx", "wb").write(entry(1, 64, 100) + entry(2, 128, 200))
+    open(base + ".ecj", "wb").write((2).to_bytes(8, "big"))
+    ec.WriteIdxFileFromEcIndex(base)
+    got = sizes(open(base + ".idx", "rb").read())
+    assert len(got) == 3 and got[2][0] == 2 and got[2][1] < 0            # 2 from .ecx + 1 deletion record
+
+
+def test_decode_with_non_empty_ecj_all_deleted(swec, tmp_path):
+    ec = swec.erasure_coding
+    base = str(tmp_path / "test_1")
+    open(base + ".ecx", "wb").write(entry(1, 64, 100) + entry(2, 128, 200))
+    open(base + ".ecj", "wb").write((1).to_bytes(8, "big") + (2).to_bytes(8, "big"))
+    assert ec.HasLiveNeedles(base) is True                               # before the merge
+    ec.RebuildEcxFile(base)
+    assert not os.path.exists(base + ".ecj")
+    assert ec.HasLiveNeedles(base) is False
+    ec.WriteIdxFileFromEcIndex(base)
+    got = sizes(open(base + ".idx", "rb").read())
+    assert len(got) == 2 and all(s < 0 for _, s in got)
+
+
+def test_decode_with_non_empty_ecj_partially_deleted(swec, tmp_path):
+    ec = swec.erasure_coding
+    base = str(tmp_path / "test_1")
+    open(base + ".ecx", "wb").write(entry(1, 64, 100) + entry(2, 128, 200) + entry(3, 256, 300))
+    open(base + ".ecj", "wb").write((2).to_bytes(8, "big"))
+    ec.RebuildEcxFile(base)
+    assert ec.HasLiveNeedles(base) is True
+    ec.WriteIdxFileFromEcIndex(base)
+    got = dict(sizes(open(base + ".idx", "rb").read()))
+    assert len(got) == 3 and got[1] == 100 and got[3] == 300 and got[2] < 0
+
+
+@pytest.mark.parametrize("ecj", [b"", None], ids=["empty_ecj", "no_ecj_file"])
+def test_decode_with_empty_or_missing_ecj(swec, tmp_path, ecj):
+    """TestDecodeWithEmptyEcj / TestDecodeWithNoEcjFile: nothing to merge, everything stays live."""
+    ec = swec.erasure_coding
+    base = str(tmp_path / "test_1")
+    ecx = entry(1, 64, 100) + entry(2, 128, 200)
+    open(base + ".ecx", "wb").write(ecx)
+    if ecj is not None:
+        open(base + ".ecj", "wb").write(ecj)
+    ec.RebuildEcxFile(base)
+    assert open(base + ".ecx", "rb").read() == ecx and ec.HasLiveNeedles(base) is True
+    ec.WriteIdxFileFromEcIndex(base)
+    assert open(base + ".idx", "rb").read() == ecx
