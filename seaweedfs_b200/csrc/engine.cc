@@ -613,9 +613,10 @@ int swec_device_count(int* count) {
     int n = 0;
     const cudaError_t e = cudaGetDeviceCount(&n);
     if (count) *count = e == cudaSuccess ? n : 0;
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess) {  // whatever the driver's reason, the caller's answer is the same: no device
         cudaGetLastError();
-        return cuda_fail(e, "cudaGetDeviceCount") == SWEC_ERR_CUDA ? SWEC_ERR_NO_DEVICE : SWEC_ERR_NO_DEVICE;
+        cuda_fail(e, "cudaGetDeviceCount");  // records the detail text
+        return SWEC_ERR_NO_DEVICE;
     }
     return n > 0 ? SWEC_OK : fail(SWEC_ERR_NO_DEVICE, "no CUDA devices");
 }
