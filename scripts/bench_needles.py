@@ -51,9 +51,9 @@ def main():
                 ec.ReadEcShardNeedles(base, [nid], capacity=CAP)
             t_single, l_single = (time.perf_counter() - t0) / len(sample), (L.swec_kernel_launches() - l0) / len(sample)
             vol = ec.EcVolume(base)
-            vol.ReadEcShardNeedles(ids[:8], capacity=CAP)
+            vol.ReadEcShardNeedles(ids)                                  # grows the staging ring once
             t0 = time.perf_counter()
-            out2 = vol.ReadEcShardNeedles(ids, capacity=CAP)
+            out2 = vol.ReadEcShardNeedles(ids)                           # steady state, exact-size arena (two passes)
             t_mounted_batch = time.perf_counter() - t0
             assert all((a["bytes"] == b["bytes"]).all() for a, b in zip(out, out2))
             t0 = time.perf_counter()

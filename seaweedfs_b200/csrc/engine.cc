@@ -502,6 +502,12 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
     return rc;
 }
 
+// Largest interval the packed path takes (bigger ones stream through apply_host): small on purpose — the
+// ring behind it is 3 slots x (k+2m) streams x this, and needle-sized intervals gain nothing from more.
+static size_t packed_max_bytes() {
+    return std::min(size_t(std::max(4096l, g_opt_stage_chunk.load())), size_t(2) << 20);
+}
+
 // Many small intervals that share one matrix (degraded reads behind one dead server): pack them
 // back to back (each padded to 16 bytes) into slot-sized launches so the per-call costs — stream
 // round trip, launch, DMA set-up — are paid once per ~chunk instead of once per needle.
@@ -519,7 +525,7 @@ static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std
     if (rc) return rc;
     // size the ring for THIS batch (a lone degraded read must not pin 3 x 18 x 16 MiB): everything packed
     // back to back, capped by the configured chunk; ensure_slots only ever grows an existing ring
-    const size_t max_chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
+    const size_t max_chunk = packed_max_bytes();
     size_t packed = 0;
     for (const Segment& sg : segs) packed += (sg.len + 15) & ~size_t(15);
     const size_t chunk = std::min(max_chunk, (packed + 65535) & ~size_t(65535));
@@ -725,7 +731,7 @@ int swec_reconstruct(swec_encoder* e, uint8_t* const* shards, const uint8_t* pre
 int swec_reconstruct_batch(swec_encoder* e, const swec_reconstruct_item* items, int n_items) {
     if (!e || (n_items > 0 && !items)) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
     const int total = e->k + e->m;
-    const size_t chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
+    const size_t chunk = swec::packed_max_bytes();
     // group by (presence mask, data_only); big items take the ordinary streaming path
     struct Group {
         std::vector<int> ins, outs;

@@ -323,18 +323,35 @@ def volume_ec_shards_to_volume(data_base_file_name: str, index_base_file_name: s
     return int(size.value)
 
 
-def _needle_reads(needle_ids, capacity):
+def _needle_reads(needle_ids, capacity, sizes=None):
+    """capacity: fixed bytes per needle, or None with `sizes` (exact bytes per needle from a sizing pass)."""
     reads = (NeedleRead * len(needle_ids))()
-    arena = np.empty(max(1, len(needle_ids)) * capacity, dtype=np.uint8)      # untouched pages cost nothing
+    caps = [capacity] * len(needle_ids) if sizes is None else list(sizes)
+    starts = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+    arena = np.empty(max(1, int(starts[-1])), dtype=np.uint8)
     for j, (r, nid) in enumerate(zip(reads, needle_ids)):
-        r.needle_id, r.buf, r.capacity = nid, arena.ctypes.data + j * capacity, capacity
-    return reads, arena
+        r.needle_id, r.buf, r.capacity = nid, arena.ctypes.data + int(starts[j]), caps[j]
+    return reads, arena, starts
 
 
-def _needle_results(reads, arena, capacity):
+def _needle_results(reads, arena, starts):
     return [{"id": r.needle_id, "status": STATUS.get(r.status, str(r.status)), "offset": r.offset, "size": r.size,
-             "bytes": arena[j * capacity: j * capacity + r.n_bytes].copy() if r.status == 0 else None,
+             "bytes": arena[int(starts[j]): int(starts[j]) + r.n_bytes] if r.status == 0 else None,
              "n_bytes": r.n_bytes, "recovered_intervals": r.n_recovered_intervals} for j, r in enumerate(reads)]
+
+
+def _read_needles(call, needle_ids, capacity):
+    """capacity None ⇒ two passes: a sizing pass with zero-capacity buffers (every live needle answers
+    SWEC_ERR_INVALID_ARG with the bytes it needs, nothing is read), then the real one into an exact arena."""
+    if capacity is None:
+        reads, arena, starts = _needle_reads(needle_ids, 0)
+        check(call(reads, len(needle_ids)))
+        sizes = [r.n_bytes if r.status == -1 else 0 for r in reads]
+        reads, arena, starts = _needle_reads(needle_ids, None, sizes)
+    else:
+        reads, arena, starts = _needle_reads(needle_ids, capacity)
+    check(call(reads, len(needle_ids)))
+    return _needle_results(reads, arena, starts)
 
 
 class EcVolume:
@@ -350,10 +367,8 @@ class EcVolume:
                                         device, C.byref(h)))
         self._h = h
 
-    def read_needles(self, needle_ids: list[int], capacity: int = 1 << 20):
-        reads, arena = _needle_reads(needle_ids, capacity)
-        check(lib().swec_ec_volume_read_needles(self._h, reads, len(needle_ids)))
-        return _needle_results(reads, arena, capacity)
+    def read_needles(self, needle_ids: list[int], capacity: int | None = None):
+        return _read_needles(lambda reads, n: lib().swec_ec_volume_read_needles(self._h, reads, n), needle_ids, capacity)
 
     def delete_needle(self, needle_id: int) -> None:
         """DeleteNeedleFromEcx (ec_volume_delete.go:28-93)"""
@@ -371,14 +386,13 @@ class EcVolume:
 
 
 def read_ec_shard_needles(data_base_file_name: str, needle_ids: list[int], index_base_file_name: str | None = None,
-                          additional_dirs: list[str] | None = None, device: int = 0, capacity: int = 1 << 20):
+                          additional_dirs: list[str] | None = None, device: int = 0, capacity: int | None = None):
     """One-shot form: mount, read, unmount.  Returns one dict per id with status name, offset, size, the raw
     record bytes and how many intervals had to be reconstructed."""
     arr, n = _dirs(additional_dirs)
-    reads, arena = _needle_reads(needle_ids, capacity)
-    check(lib().swec_read_ec_needles(data_base_file_name.encode(), (index_base_file_name or "").encode(), arr, n,
-                                     reads, len(needle_ids), device))
-    return _needle_results(reads, arena, capacity)
+    return _read_needles(lambda reads, cnt: lib().swec_read_ec_needles(
+        data_base_file_name.encode(), (index_base_file_name or "").encode(), arr, n, reads, cnt, device),
+        needle_ids, capacity)
 
 
 ReadEcShardNeedles = read_ec_shard_needles
