@@ -240,7 +240,7 @@ std::string generate_combine(const Matrix& rows, const std::string& struct_name,
             std::string nxt = em.tmp();
             stats.xtime_steps++;
             if (terms.empty()) {
-                em.os << "    const u32 " << nxt << " = SWEC_XT0(" << acc << ");\n";
+                em.os << "    const u32 " << nxt << " = SWEC_XT0" << ((stats.xtime_steps & 1) ? "B" : "A") << "(" << acc << ");\n";
             } else {
                 // first term rides in the step's final 3-input XOR; the rest are folded off the
                 // accumulator's dependency chain first
@@ -252,7 +252,9 @@ std::string generate_combine(const Matrix& rows, const std::string& struct_name,
                     std::string folded = em.xor_all(head);
                     terms = {folded, terms.back()};
                 }
-                em.os << "    const u32 " << nxt << "_ = SWEC_XT1(" << acc << ", " << first << ");\n";
+                // steps alternate between the A and B spelling so that a build may give them different
+                // instruction mixes (device_common.cuh, SWEC_XT_VARIANT 3); otherwise A == B
+                em.os << "    const u32 " << nxt << "_ = SWEC_XT1" << ((stats.xtime_steps & 1) ? "B" : "A") << "(" << acc << ", " << first << ");\n";
                 if (terms.empty()) {
                     em.os << "    const u32 " << nxt << " = " << nxt << "_;\n";
                 } else if (terms.size() == 1) {

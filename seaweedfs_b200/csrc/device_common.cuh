@@ -25,22 +25,43 @@ __device__ __forceinline__ u32 swec_x3(u32 a, u32 b, u32 c) {
 //   b2  = 2*(a - hi) = 2a - 2hi                   (two IMADs, fma pipe)   — bytes shifted left
 //   out = b2 ^ m ^ s                              (one LOP3, alu pipe)
 // Two alu-pipe and three fma-pipe instructions per step: the integer-ALU pipe is the scarce one.
-__device__ __forceinline__ u32 swec_xt1(u32 a, u32 s) {
+// Variants of the step (SWEC_XT_VARIANT; the arithmetic is identical, the instruction mix is not):
+//   0  hi = a & 0x80..; m = mulhi(hi, 0x1D<<25); b2 = 2a - 2hi; out = b2 ^ m ^ s      2 alu + 3 fma   (5 instr)
+//   1  shift-based                                                                    4 alu + 1 fma   (5 instr)
+//   2  mask = prmt(a) (msb of every byte replicated over the byte); a2 = 2a;
+//      out = ((a2 & 0xFE..) ^ s) ^ (mask & 0x1D..)                                    3 alu + 1 fma   (4 instr)
+//   3  call sites alternate between 0 and 2: 5 alu + 4 fma per two steps (9 instr) — neither pipe ahead
+template <int V>
+__device__ __forceinline__ u32 swec_xt1_v(u32 a, u32 s) {
+    if (V == 2) {
+        u32 mask, a2, u, r;
+        asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(mask) : "r"(a));
+        asm("mul.lo.u32 %0, %1, 2;" : "=r"(a2) : "r"(a));
+        asm("lop3.b32 %0, %1, 0xfefefefe, %2, 0x6a;" : "=r"(u) : "r"(a2), "r"(s));     // (a2 & c) ^ s
+        asm("lop3.b32 %0, %1, 0x1d1d1d1d, %2, 0x6a;" : "=r"(r) : "r"(mask), "r"(u));   // (mask & c) ^ u
+        return r;
+    }
     const u32 hi = a & 0x80808080u;
-#if SWEC_XT_VARIANT == 1
-    // shift-based variant (all alu pipe except the multiply)
-    const u32 m = (hi >> 7) * 0x1du;
-    const u32 b2 = (a ^ hi) << 1;
-#else
+    if (V == 1) {  // shift-based variant (all alu pipe except the multiply)
+        const u32 m = (hi >> 7) * 0x1du;
+        const u32 b2 = (a ^ hi) << 1;
+        return swec_x3(b2, m, s);
+    }
     u32 m, a2, b2;
     asm("mul.hi.u32 %0, %1, 0x3a000000;" : "=r"(m) : "r"(hi));
     asm("mul.lo.u32 %0, %1, 2;" : "=r"(a2) : "r"(a));
     asm("mad.lo.u32 %0, %1, 0xfffffffe, %2;" : "=r"(b2) : "r"(hi), "r"(a2));
-#endif
     return swec_x3(b2, m, s);
 }
-#define SWEC_XT1(a, s) swec_xt1((a), (s))
-#define SWEC_XT0(a) swec_xt1((a), 0u)
+#if SWEC_XT_VARIANT == 3
+#define SWEC_XT1A(a, s) swec_xt1_v<0>((a), (s))
+#define SWEC_XT1B(a, s) swec_xt1_v<2>((a), (s))
+#else
+#define SWEC_XT1A(a, s) swec_xt1_v<SWEC_XT_VARIANT>((a), (s))
+#define SWEC_XT1B(a, s) swec_xt1_v<SWEC_XT_VARIANT>((a), (s))
+#endif
+#define SWEC_XT0A(a) SWEC_XT1A((a), 0u)
+#define SWEC_XT0B(a) SWEC_XT1B((a), 0u)
 
 // ---- streaming 16-byte global accesses (read-once / write-once data: keep it out of L1) -----
 #ifndef SWEC_LD_POLICY

@@ -242,7 +242,7 @@ int swec_encoder_impl::get_tables(const Matrix& rows, DeviceTables* out, cudaStr
 // ------------------------------------------------------------------ matrix → kernel dispatch
 
 static bool is_rs10x4_parity(const swec_encoder_impl& e, const Matrix& rows) {
-    if (!e.rs10x4 || rows.rows != 4 || rows.cols != 10) return false;
+    if (!e.rs10x4 || rows.rows != 4 || rows.cols != 10 || !g_opt_use_aot.load()) return false;
     for (int r = 0; r < 4; r++)
         if (memcmp(rows.row(r), e.gen.row(10 + r), 10) != 0) return false;
     return true;
@@ -648,6 +648,8 @@ int swec_set_option(const char* name, long value) {
     else if (n == "stage_slots" && value >= 2 && value <= 16) g_opt_stage_slots = value;
     else if (n == "jit_min_bytes" && value >= 0) g_opt_jit_min_bytes = value;
     else if (n == "jit" && (value == 0 || value == 1)) g_opt_jit_enabled = value;
+    else if (n == "xt_variant" && value >= 0 && value <= 3) g_opt_xt_variant = value;
+    else if (n == "use_aot" && (value == 0 || value == 1)) g_opt_use_aot = value;
     else return fail(SWEC_ERR_INVALID_ARG, "unknown option or value out of range: " + n);
     return SWEC_OK;
 }

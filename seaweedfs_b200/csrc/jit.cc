@@ -144,7 +144,8 @@ bool jit_available() { return nvrtc().ok; }
 void jit_shutdown() { jit_stop_at_exit(); }
 
 static std::vector<uint8_t> jit_key(const Matrix& rows, int threads, int unroll) {
-    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols), uint8_t(threads / 64), uint8_t(unroll)};
+    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols), uint8_t(threads / 64), uint8_t(unroll),
+                             uint8_t(g_opt_xt_variant.load())};
     key.insert(key.end(), rows.v.begin(), rows.v.end());
     return key;
 }
@@ -159,7 +160,7 @@ static int compile_cubin(const Matrix& rows, int threads, int unroll, std::vecto
     if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
     if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
     const std::string T = std::to_string(threads), U = std::to_string(unroll);
-    std::string src = "#define SWEC_XT_VARIANT 0\n";
+    std::string src = "#define SWEC_XT_VARIANT " + std::to_string(int(g_opt_xt_variant.load())) + "\n";
     src += kDeviceCommonSrc;
     src += generate_combine(rows, "SwecJit", CodegenOptions{}, stats);
     src +=

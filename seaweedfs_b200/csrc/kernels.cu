@@ -229,6 +229,8 @@ static long env_long(const char* name, long dflt) {
 std::atomic<long> g_opt_enc_threads{env_long("SWEC_ENC_THREADS", 512)};
 std::atomic<long> g_opt_enc_unroll{env_long("SWEC_ENC_UNROLL", 2)};
 std::atomic<long> g_opt_ctas_per_sm{env_long("SWEC_CTAS_PER_SM", 0)};  // 0 = derive from the shape
+std::atomic<long> g_opt_xt_variant{env_long("SWEC_XT_VARIANT_JIT", SWEC_XT_VARIANT)};
+std::atomic<long> g_opt_use_aot{env_long("SWEC_USE_AOT", 1)};
 
 int encode_ctas_per_sm() {
     const long c = g_opt_ctas_per_sm.load();

@@ -13,6 +13,9 @@ extern std::atomic<unsigned long long> g_kernel_launches;
 // tuning knobs: launch shape of the Horner kernels (swec_set_option / SWEC_ENC_THREADS, SWEC_ENC_UNROLL,
 // SWEC_CTAS_PER_SM).  ctas_per_sm = resident CTAs per SM the persistent grids are sized for.
 extern std::atomic<long> g_opt_enc_threads, g_opt_enc_unroll, g_opt_ctas_per_sm;
+// measurement knobs: xtime instruction-mix variant of run-time specialised kernels (device_common.cuh), and
+// whether RS(10,4) encode takes the ahead-of-time kernel (1) or is specialised at run time like any matrix (0)
+extern std::atomic<long> g_opt_xt_variant, g_opt_use_aot;
 int encode_ctas_per_sm();
 
 cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStream_t s);

@@ -19,8 +19,10 @@ typedef uint32_t u32;
 #define SWEC_X2(a,b) ((a)^(b))
 #define SWEC_X3(a,b,c) ((a)^(b)^(c))
 static inline u32 xt(u32 a){ u32 hi=a&0x80808080u; return ((a^hi)<<1) ^ ((hi>>7)*0x1du); }
-#define SWEC_XT0(a) xt(a)
-#define SWEC_XT1(a,s) (xt(a)^(s))
+#define SWEC_XT0A(a) xt(a)
+#define SWEC_XT0B(a) xt(a)
+#define SWEC_XT1A(a,s) (xt(a)^(s))
+#define SWEC_XT1B(a,s) (xt(a)^(s))
 #include "gen.inc"
 int main(){
   u32 x[G::K], y[G::R];
