@@ -63,6 +63,9 @@ def generate() -> None:
                          stdout=subprocess.PIPE, text=True).stdout
     with open(os.path.join(GEN, "gen_rs10x4_encode.inc"), "w") as f:
         f.write(out)
+    # the same combiner under a second name: kernels.cu binds it to the low-power multiply-by-2 step
+    with open(os.path.join(GEN, "gen_rs10x4_encode_lp.inc"), "w") as f:
+        f.write(out.replace("struct Rs10x4Encode ", "struct Rs10x4EncodeLP "))
     # JIT prelude: the two device headers, flattened (NVRTC cannot #include from disk)
     text = []
     for name in ("apply_params.h", "device_common.cuh"):

@@ -85,7 +85,7 @@ struct JitEntry {
 struct JitRequest {
     Matrix rows;
     std::vector<uint8_t> key;
-    int threads, unroll, device;
+    int threads, unroll, device, variant;
 };
 // Process-wide state.  Deliberately leaked (never destroyed): the compiler thread may still be
 // finishing when static destructors run at process exit and must find the map and mutex alive.
@@ -104,7 +104,7 @@ JitGlobal& G() {
 constexpr int kHotUses = 2;        // a matrix is worth a background compile from its 2nd short use
 constexpr size_t kMaxQueued = 16;  // beyond that the table kernel keeps serving
 
-std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll);
+std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll, int variant);
 
 void jit_worker_loop() {
     JitGlobal& g = G();
@@ -117,7 +117,7 @@ void jit_worker_loop() {
         g.cache[rq.key].state = JitEntry::kCompiling;
         lock.unlock();
         cudaSetDevice(rq.device);
-        auto k = build_kernel(rq.rows, rq.threads, rq.unroll);
+        auto k = build_kernel(rq.rows, rq.threads, rq.unroll, rq.variant);
         lock.lock();
         g.cache[rq.key].kernel = k;
         g.cache[rq.key].state = k ? JitEntry::kReady : JitEntry::kFailed;
@@ -143,24 +143,23 @@ bool jit_available() { return nvrtc().ok; }
 
 void jit_shutdown() { jit_stop_at_exit(); }
 
-static std::vector<uint8_t> jit_key(const Matrix& rows, int threads, int unroll) {
-    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols), uint8_t(threads / 64), uint8_t(unroll),
-                             uint8_t(g_opt_xt_variant.load())};
+static std::vector<uint8_t> jit_key(const Matrix& rows, int threads, int unroll, int variant) {
+    std::vector<uint8_t> key{uint8_t(rows.rows), uint8_t(rows.cols), uint8_t(threads / 64), uint8_t(unroll), uint8_t(variant)};
     key.insert(key.end(), rows.v.begin(), rows.v.end());
     return key;
 }
 
 bool jit_cached(swec_encoder_impl* enc, const Matrix& rows) {
-    return enc->jit.count(jit_key(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()))) != 0;
+    return enc->jit.count(jit_key(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()), effective_xt_variant())) != 0;
 }
 
 // generate + NVRTC-compile the specialised kernels for `rows`; no CUDA context needed
-static int compile_cubin(const Matrix& rows, int threads, int unroll, std::vector<char>* cubin, CodegenStats* stats) {
+static int compile_cubin(const Matrix& rows, int threads, int unroll, int variant, std::vector<char>* cubin, CodegenStats* stats) {
     Nvrtc& n = nvrtc();
     if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
     if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
     const std::string T = std::to_string(threads), U = std::to_string(unroll);
-    std::string src = "#define SWEC_XT_VARIANT " + std::to_string(int(g_opt_xt_variant.load())) + "\n";
+    std::string src = "#define SWEC_XT_VARIANT " + std::to_string(variant) + "\n";
     src += kDeviceCommonSrc;
     src += generate_combine(rows, "SwecJit", CodegenOptions{}, stats);
     src +=
@@ -192,12 +191,12 @@ static int compile_cubin(const Matrix& rows, int threads, int unroll, std::vecto
 }
 
 namespace {
-std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll) {
+std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll, int variant) {
     auto kernel = std::make_shared<JitKernel>();
     kernel->threads = threads;
     kernel->unroll = unroll;
     std::vector<char> cubin;
-    if (compile_cubin(rows, threads, unroll, &cubin, &kernel->stats) != SWEC_OK) return nullptr;
+    if (compile_cubin(rows, threads, unroll, variant, &cubin, &kernel->stats) != SWEC_OK) return nullptr;
     cudaError_t e = cudaLibraryLoadData(&kernel->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->flat, kernel->lib, "swec_jit_flat");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->blocked, kernel->lib, "swec_jit_blocked");
@@ -215,7 +214,8 @@ std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unr
 // behind one dead server) is compiled once by the background worker and picked up when ready.
 int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait) {
     const int threads = int(g_opt_enc_threads.load()), unroll = int(g_opt_enc_unroll.load());
-    const std::vector<uint8_t> key = jit_key(rows, threads, unroll);
+    const int variant = effective_xt_variant();  // boost-clock or low-power step, by the device's recent load
+    const std::vector<uint8_t> key = jit_key(rows, threads, unroll, variant);
     *out = nullptr;
     auto local = enc->jit.find(key);
     if (local != enc->jit.end()) {
@@ -237,7 +237,7 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
                 int dev = 0;
                 cudaGetDevice(&dev);
                 e.state = JitEntry::kQueued;
-                g.queue.push_back({rows, key, threads, unroll, dev});
+                g.queue.push_back({rows, key, threads, unroll, dev, variant});
                 if (!g.worker_started) {
                     g.worker_started = true;
                     g.worker = std::thread(jit_worker_loop);
@@ -260,7 +260,7 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
         }
         e.state = JitEntry::kCompiling;
         lock.unlock();
-        auto k = build_kernel(rows, threads, unroll);
+        auto k = build_kernel(rows, threads, unroll, variant);
         lock.lock();
         JitEntry& e2 = g.cache[key];
         e2.kernel = k;
@@ -275,7 +275,7 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
 int jit_debug_compile(const Matrix& rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
     std::vector<char> cubin;
     CodegenStats st;
-    const int rc = compile_cubin(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()), &cubin, &st);
+    const int rc = compile_cubin(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()), effective_xt_variant(), &cubin, &st);
     if (cubin_bytes) *cubin_bytes = cubin.size();
     if (xtime_steps) *xtime_steps = st.xtime_steps;
     if (xor_ops) *xor_ops = st.xor_ops;
@@ -292,6 +292,7 @@ cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocke
     const u64 cap = u64(sms) * u64(encode_ctas_per_sm());
     const unsigned grid = unsigned(need < cap ? need : cap);
     void* args[] = {const_cast<SwecApplyParams*>(&p)};
+    note_kernel_work(double(p.nvec) * 16.0 * 14.0 / 6.2e9 * 1e3);  // ≈ k + r streams; feeds the power policy
     g_kernel_launches++;
     return cudaLaunchKernel(reinterpret_cast<const void*>(blocked ? k.blocked : k.flat), dim3(grid),
                             dim3(unsigned(k.threads)), args, 0, s);

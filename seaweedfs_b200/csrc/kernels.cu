@@ -21,7 +21,21 @@
 #endif
 #include "device_common.cuh"
 #include "gen_rs10x4_encode.inc"
+// the same combiner once more with the low-power step (variant 2) bound to both spellings
+#undef SWEC_XT1A
+#undef SWEC_XT1B
+#define SWEC_XT1A(a, s) swec_xt1_v<2>((a), (s))
+#define SWEC_XT1B(a, s) swec_xt1_v<2>((a), (s))
+#include "gen_rs10x4_encode_lp.inc"
+#undef SWEC_XT1A
+#undef SWEC_XT1B
+#define SWEC_XT1A(a, s) swec_xt1_v<SWEC_XT_VARIANT>((a), (s))
+#define SWEC_XT1B(a, s) swec_xt1_v<SWEC_XT_VARIANT>((a), (s))
 #include "kernels.h"
+
+#include <chrono>
+#include <cmath>
+#include <mutex>
 
 namespace swec {
 
@@ -31,9 +45,10 @@ std::atomic<unsigned long long> g_kernel_launches{0};
 
 // Launch shape is a tuning surface (threads per CTA × column slices per thread); the default is the
 // measured best, SWEC_ENC_THREADS / SWEC_ENC_UNROLL select the others for sweeps.
-template <int THREADS, int UNROLL, bool BLOCKED>
+template <int THREADS, int UNROLL, bool BLOCKED, bool LOW_POWER = false>
 __global__ void __launch_bounds__(THREADS) rs10x4_encode(const __grid_constant__ SwecApplyParams p) {
-    swec_horner_body<Rs10x4Encode, BLOCKED, UNROLL>(p);
+    if (LOW_POWER) swec_horner_body<Rs10x4EncodeLP, BLOCKED, UNROLL>(p);
+    else swec_horner_body<Rs10x4Encode, BLOCKED, UNROLL>(p);
 }
 
 // ------------------------------------------------------------------ run-time matrix, smem tables
@@ -231,6 +246,57 @@ std::atomic<long> g_opt_enc_unroll{env_long("SWEC_ENC_UNROLL", 2)};
 std::atomic<long> g_opt_ctas_per_sm{env_long("SWEC_CTAS_PER_SM", 0)};  // 0 = derive from the shape
 std::atomic<long> g_opt_xt_variant{env_long("SWEC_XT_VARIANT_JIT", SWEC_XT_VARIANT)};
 std::atomic<long> g_opt_use_aot{env_long("SWEC_USE_AOT", 1)};
+std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 0)};
+
+// ---- power policy: "heat" = kernel milliseconds recently spent on the device, decaying with a 1 s time
+// constant.  Continuous encoding drives it towards 1000 x duty cycle; a 13-launch burst leaves it below 100.
+namespace {
+struct Heat {
+    std::mutex mu;
+    double level = 0;
+    std::chrono::steady_clock::time_point last{};
+};
+Heat g_heat[64];
+constexpr double kHeatTauMs = 1000.0, kHeatHotMs = 250.0;
+Heat& heat_here() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_heat[(dev >= 0 && dev < 64) ? dev : 0];
+}
+double decayed(Heat& h, std::chrono::steady_clock::time_point now) {
+    if (h.last.time_since_epoch().count() == 0) return 0;
+    const double dt = std::chrono::duration<double, std::milli>(now - h.last).count();
+    return h.level * std::exp(-dt / kHeatTauMs);
+}
+}  // namespace
+
+void note_kernel_work(double est_ms) {
+    Heat& h = heat_here();
+    const auto now = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lk(h.mu);
+    h.level = decayed(h, now) + est_ms;
+    h.last = now;
+}
+
+bool low_power_now() {
+    const long mode = g_opt_power_mode.load();
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    Heat& h = heat_here();
+    const auto now = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lk(h.mu);
+    return decayed(h, now) > kHeatHotMs;
+}
+
+int effective_xt_variant() {
+    const long v = g_opt_xt_variant.load();
+    if (v != 0) return int(v);          // explicit measurement override
+    return low_power_now() ? 2 : 0;
+}
+
+static double est_ms_for(const SwecApplyParams& p, int k, int r) {
+    return double(p.nvec) * 16.0 * double(k + r) / 6.2e9 * 1e3;   // algorithmic bytes at ~6.2 TB/s
+}
 
 int encode_ctas_per_sm() {
     const long c = g_opt_ctas_per_sm.load();
@@ -245,8 +311,12 @@ int encode_ctas_per_sm() {
 template <int THREADS, int UNROLL>
 static cudaError_t launch_rs10x4_shape(const SwecApplyParams& p, bool blocked, int ctas_per_sm, cudaStream_t s) {
     const unsigned grid = grid_for((p.nvec + UNROLL - 1) / UNROLL, THREADS, ctas_per_sm);
-    if (blocked) rs10x4_encode<THREADS, UNROLL, true><<<grid, THREADS, 0, s>>>(p);
-    else rs10x4_encode<THREADS, UNROLL, false><<<grid, THREADS, 0, s>>>(p);
+    const bool lp = low_power_now();
+    note_kernel_work(est_ms_for(p, 10, 4));
+    if (blocked && lp) rs10x4_encode<THREADS, UNROLL, true, true><<<grid, THREADS, 0, s>>>(p);
+    else if (blocked) rs10x4_encode<THREADS, UNROLL, true, false><<<grid, THREADS, 0, s>>>(p);
+    else if (lp) rs10x4_encode<THREADS, UNROLL, false, true><<<grid, THREADS, 0, s>>>(p);
+    else rs10x4_encode<THREADS, UNROLL, false, false><<<grid, THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

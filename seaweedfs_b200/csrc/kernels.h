@@ -16,6 +16,15 @@ extern std::atomic<long> g_opt_enc_threads, g_opt_enc_unroll, g_opt_ctas_per_sm;
 // measurement knobs: xtime instruction-mix variant of run-time specialised kernels (device_common.cuh), and
 // whether RS(10,4) encode takes the ahead-of-time kernel (1) or is specialised at run time like any matrix (0)
 extern std::atomic<long> g_opt_xt_variant, g_opt_use_aot;
+// Power policy (profiles/r01z_xt_variant_probe*.jsonl).  A B200 that encodes back to back for
+// more than a few hundred ms runs into its 1,000 W cap and drops the SM clock to ~1.45 GHz; from then on the
+// 4-instruction multiply-by-2 step (variant 2: fewer instructions, far fewer IMADs) is 4-5 % FASTER than the
+// 5-instruction one that wins while the GPU still boosts.  "power_mode": 0 = auto (switch by recent kernel
+// work on the device), 1 = always the boost-clock variant, 2 = always the low-power variant.
+extern std::atomic<long> g_opt_power_mode;
+void note_kernel_work(double est_ms);   // called by every Horner launch: feeds the auto policy
+bool low_power_now();                   // which variant the next Horner launch on the current device takes
+int effective_xt_variant();             // variant for run-time specialised kernels (explicit xt_variant wins)
 int encode_ctas_per_sm();
 
 cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStream_t s);

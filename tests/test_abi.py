@@ -142,6 +142,17 @@ def test_argument_validation(swec, tmp_path):
     assert e.value.name == "SWEC_ERR_IO"
 
 
+def test_set_option_validation(swec):
+    L = swec.lib()
+    for name, good, bad in ((b"power_mode", 2, 3), (b"xt_variant", 3, 4), (b"use_aot", 0, 2), (b"stage_slots", 4, 1),
+                            (b"enc_threads", 256, 300), (b"jit", 1, 5)):
+        assert L.swec_set_option(name, bad) == -1, name
+        assert L.swec_set_option(name, good) == 0, name
+    assert L.swec_set_option(b"no_such_option", 1) == -1 and L.swec_set_option(None, 1) == -1
+    for name, dflt in ((b"power_mode", 0), (b"xt_variant", 0), (b"use_aot", 1), (b"stage_slots", 3), (b"enc_threads", 512)):
+        assert L.swec_set_option(name, dflt) == 0
+
+
 def test_multi_handle_argument_validation(swec):
     """The column-split calls validate the group before touching a device."""
     ec = swec.erasure_coding

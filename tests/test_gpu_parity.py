@@ -667,3 +667,36 @@ def test_north_star_roofline_target(cuda, swec):
     print(f"encode {gib} GiB: {ms:.3f} ms, {size / ms / 1e6:.0f} GB/s input, {frac:.3f} of HBM peak")
     assert frac >= 0.70, frac
     enc.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 0])
+def test_power_mode_variants_are_bit_exact(cuda, swec, oracle, mode):
+    """"power_mode" picks between two instruction mixes of the same arithmetic (boost-clock / low-power step,
+    device_common.cuh): RS(10,4) encode (AOT kernels), a custom ratio and a worst-case reconstruct (run-time
+    specialised kernels) must not change by a bit."""
+    torch = cuda
+    L = swec.lib()
+    assert L.swec_set_option(b"power_mode", mode) == 0
+    try:
+        n = 5 * (1 << 20) + 48
+        rng = np.random.default_rng(mode)
+        for k, m in ((10, 4), (6, 3)):
+            e = swec.erasure_coding.Encoder(k, m, device=0)
+            data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(k)]
+            want = oracle.encode(k, m, data)
+            d = [dev(torch, x) for x in data]
+            p = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(m)]
+            for _ in range(2):
+                e.encode_device([t.data_ptr() for t in d], [t.data_ptr() for t in p], n, stream(torch))
+            torch.cuda.synchronize()
+            for got, w in zip(p, want):
+                assert (got.cpu().numpy() == w).all(), (mode, k, m)
+            # erase the first m shards, rebuild them on the device (long stream ⇒ specialised kernel)
+            allsh = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(m)] + d[m:] + p
+            e.reconstruct_device([t.data_ptr() for t in allsh], [0] * m + [1] * k, n, False, stream(torch))
+            torch.cuda.synchronize()
+            for i in range(m):
+                assert (allsh[i].cpu().numpy() == data[i]).all(), (mode, k, m, i)
+            e.close()
+    finally:
+        L.swec_set_option(b"power_mode", 0)
