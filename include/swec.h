@@ -75,9 +75,9 @@ uint64_t swec_kernel_launches(void);          /* kernels this process has launch
 /* Tuning: "enc_threads" {128,256,512}, "enc_unroll" {1,2}, "ctas_per_sm" (0 = auto),
  * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "jit" {0,1},
  * "jit_min_bytes" (streams at least this long compile their kernel inline, shorter ones in the
- * background), "power_mode" {0 = auto, 1 = always the boost-clock kernel variant, 2 = always the low-power
- * one — a GPU that encodes back to back for more than ~0.3 s sits on its power cap, where the variant with
- * fewer instructions is 4-5 % faster; auto switches by the device's recent kernel time}.  Measurement knobs: "xt_variant" {0..3} (instruction mix of run-time specialised kernels,
+ * background), "power_mode" {1 = always the boost-clock kernel variant (default), 2 = always the
+ * low-power one, 0 = auto by the device's recent kernel time — a GPU that runs encode launches back to back
+ * for more than ~0.3 s sits on its power cap, where the variant with fewer instructions is 4-5 % faster}.  Measurement knobs: "xt_variant" {0..3} (instruction mix of run-time specialised kernels,
  * device_common.cuh), "use_aot" {0,1} (0: RS(10,4) encode is specialised at run time like any matrix).     */
 int swec_set_option(const char *name, long value);
 /* Diagnostics: generate and NVRTC-compile (sm_100a) the specialised kernel for an r×k matrix without

@@ -246,10 +246,13 @@ std::atomic<long> g_opt_enc_unroll{env_long("SWEC_ENC_UNROLL", 2)};
 std::atomic<long> g_opt_ctas_per_sm{env_long("SWEC_CTAS_PER_SM", 0)};  // 0 = derive from the shape
 std::atomic<long> g_opt_xt_variant{env_long("SWEC_XT_VARIANT_JIT", SWEC_XT_VARIANT)};
 std::atomic<long> g_opt_use_aot{env_long("SWEC_USE_AOT", 1)};
-std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 0)};
+std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 1)};
 
 // ---- power policy: "heat" = kernel milliseconds recently spent on the device, decaying with a 1 s time
 // constant.  Continuous encoding drives it towards 1000 x duty cycle; a 13-launch burst leaves it below 100.
+// Measured (profiles/r01z_xt_variant_*.jsonl, r01z_batch256_power_modes.txt): the low-power variant wins 4-5 %
+// only when encode launches run back to back for longer than ~0.3 s; with other kernels in between (the
+// 256-volume batch: 38 % duty) the two are equal.  Default is therefore mode 1; auto (0) is opt-in.
 namespace {
 struct Heat {
     std::mutex mu;
@@ -257,7 +260,7 @@ struct Heat {
     std::chrono::steady_clock::time_point last{};
 };
 Heat g_heat[64];
-constexpr double kHeatTauMs = 1000.0, kHeatHotMs = 250.0;
+constexpr double kHeatTauMs = 1000.0, kHeatHotMs = 600.0;  // hot = the Horner kernels own > 60 % of the last second
 Heat& heat_here() {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -19,8 +19,9 @@ extern std::atomic<long> g_opt_xt_variant, g_opt_use_aot;
 // Power policy (profiles/r01z_xt_variant_probe*.jsonl).  A B200 that encodes back to back for
 // more than a few hundred ms runs into its 1,000 W cap and drops the SM clock to ~1.45 GHz; from then on the
 // 4-instruction multiply-by-2 step (variant 2: fewer instructions, far fewer IMADs) is 4-5 % FASTER than the
-// 5-instruction one that wins while the GPU still boosts.  "power_mode": 0 = auto (switch by recent kernel
-// work on the device), 1 = always the boost-clock variant, 2 = always the low-power variant.
+// 5-instruction one that wins while the GPU still boosts.  "power_mode": 1 = always the boost-clock variant
+// (default), 2 = always the low-power variant, 0 = auto (low-power once the Horner kernels own > 60 % of the
+// device's last second).
 extern std::atomic<long> g_opt_power_mode;
 void note_kernel_work(double est_ms);   // called by every Horner launch: feeds the auto policy
 bool low_power_now();                   // which variant the next Horner launch on the current device takes

@@ -699,4 +699,4 @@ def test_power_mode_variants_are_bit_exact(cuda, swec, oracle, mode):
                 assert (allsh[i].cpu().numpy() == data[i]).all(), (mode, k, m, i)
             e.close()
     finally:
-        L.swec_set_option(b"power_mode", 0)
+        L.swec_set_option(b"power_mode", 1)
