@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reconstruct", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "swec" else args.warmup
     if args.impl == "reference":
@@ -395,38 +396,14 @@ def main():
     if args.batch_volumes > 0:
         return run_batch(args, L, enc, dat, dat_size, par, shard, stream, local, rank, world, dist, barrier)
 
-    def step():
-        enc.encode_volume_device(dat.data_ptr(), dat_size, par_ptrs, stream)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches0 = L.swec_kernel_launches()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    try:
-        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
-    except Exception:
-        gpu_uuid = None
-    with ClockSampler(local, gpu_uuid) as clk:
-        ev[0].record()
-        for i in range(args.steps):
-            step()
-            ev[i + 1].record()
-        barrier()
-    launches = L.swec_kernel_launches() - launches0
-    ms_total = ev[0].elapsed_time(ev[-1])
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * args.steps * dat_size / (ms_max / 1e3) / 1e9
-
-    # correctness outside the timed region: spot-check the parity against the oracle (rank 0)
-    checked = None
-    if rank == 0:
-        checked = f"{oracle_window_check(par, dat_size, shard, SEED0 + rank)} windows x 4 parity shards bit-exact vs oracle"
-
+    # Wake-up: from a cold process the first ~8 launches of ANY kernel run on clocks still ramping up from idle
+    # (profiles/r01z_warmup_ramp_probe.jsonl: 7.9 -> 7.0 ms over ~70 ms).  Twenty digest passes over the volume
+    # (a measurement kernel, ~120 ms of HBM reads, nothing of the path under test) take the GPU out of idle so
+    # that the W warm-up steps of each leg do what warm-up is for.  Every leg keeps its own W untimed steps and
+    # exactly K timed ones; the `sustained` leg below shows what happens when the boost window is over.
+    wake = C.c_uint64(0)
+    for _ in range(20):
+        assert L.swec_digest_device(local, dat.data_ptr(), dat_size, C.byref(wake), stream) == 0
     # ---- reconstruct, shards 0-3 erased (worst case, BASELINE configs[2]); untimed for `value` --------
     recon = None
     if not args.no_reconstruct:
@@ -465,6 +442,64 @@ def main():
                  "check": "device digests of the 4 rebuilt shards equal the originals"}
         del scratch
 
+    def step():
+        enc.encode_volume_device(dat.data_ptr(), dat_size, par_ptrs, stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = L.swec_kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local, gpu_uuid) as clk:
+        ev[0].record()
+        for i in range(args.steps):
+            step()
+            ev[i + 1].record()
+        barrier()
+    launches = L.swec_kernel_launches() - launches0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * dat_size / (ms_max / 1e3) / 1e9
+
+    # correctness outside the timed region: spot-check the parity against the oracle (rank 0)
+    checked = None
+    if rank == 0:
+        checked = f"{oracle_window_check(par, dat_size, shard, SEED0 + rank)} windows x 4 parity shards bit-exact vs oracle"
+
+
+    # ---- the same step sustained: 100 more back-to-back volumes.  The timed region above is a burst (K steps
+    # after W warm-ups, GPU at boost clocks); a B200 that keeps encoding drops its SM clock within ~0.3 s and
+    # reaches its power cap within ~1 s (profiles/r01z_xt_variant_timeline.jsonl) — reported, not hidden.
+    sustained = None
+    if not args.no_sustained:
+        n_sus = 100
+        sev = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus + 1)]
+        with ClockSampler(local, gpu_uuid) as sclk:
+            sev[0].record()
+            for i in range(n_sus):
+                step()
+                sev[i + 1].record()
+            barrier()
+        sms = [sev[i].elapsed_time(sev[i + 1]) for i in range(n_sus)]
+        tail = sum(sms[n_sus // 2:]) / (n_sus - n_sus // 2)
+        st = torch.tensor([tail], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        tail = float(st.item())
+        sc = sclk.summary()
+        sustained = {"steps": n_sus, "ms_per_step_last_half": round(tail, 4),
+                     "ms_every_10th_step": [round(x, 3) for x in sms[::10]], "ms_min": round(min(sms), 4),
+                     "value": round(world * dat_size / (tail / 1e3) / 1e9, 2), "unit": UNIT,
+                     "roofline_frac": round(1.4 * dat_size / (tail / 1e3) / 1e9 / load_peaks()[0], 4),
+                     "sm_mhz_min": sc["sm_min_mhz"], "power_w_max": sc["power_w_max"], "reasons": sc["reasons"]}
     # ---- e2e leg: Encoder.Encode on pinned host buffers (H2D + kernel + D2H timed) -----------------
     e2e = None
     if not args.no_e2e:
@@ -528,6 +563,8 @@ def main():
                 # ... and the device-resident kernel against that now CPU-verified parity, whole volume:
                 # `par` still holds encode_device() of the same 10 flat shards (reconstruct leg above)
                 if recon is not None and n == (shard & ~15):
+                    enc.encode_device([dat.data_ptr() + i * n for i in range(10)], par_ptrs, n, stream)   # flat view again
+                    torch.cuda.synchronize()
                     for p_ in range(4):
                         assert torch.equal(par[p_][:n], host[(10 + p_) * n:(11 + p_) * n].cuda()), "device parity mismatch"
                     device_full = True
@@ -564,13 +601,14 @@ def main():
                                    "(BASELINE configs[1]); 10x1 GiB large-block rows, HBM-resident",
                        "dat_bytes_per_gpu": dat_size, "shard_bytes": shard, "volumes": world,
                        "l2": "inputs (30 GiB) far exceed the 126 MB L2; no flush needed",
+                       "wake_up": "20 digest passes over the volume (~120 ms) before the legs: the GPU leaves idle clocks",
                        "seed": hex(SEED0), "check": checked},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "kernel": "rs10x4_encode_blocked", "algorithmic_bytes_per_launch": int(algo_bytes),
                          "kernel_ms": round(kernel_ms, 4)},
-            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "reconstruct": recon,
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "reconstruct": recon, "sustained": sustained,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
