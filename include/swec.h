@@ -229,6 +229,8 @@ int swec_ec_volume_read_needles(swec_ec_volume *vol, swec_needle_read *reads, in
 /* EcVolume.DeleteNeedleFromEcx (ec_volume_delete.go:28-93): append the id to the .ecj journal (fsync'ed
  * before it becomes visible to reads); unknown, tombstoned or already journalled ids are not errors.  */
 int swec_ec_volume_delete_needle(swec_ec_volume *vol, uint64_t needle_id);
+/* EcVolume.FileAndDeleteCount (ec_volume.go:330-349): .ecx entries, distinct journalled deletions.      */
+int swec_ec_volume_counts(swec_ec_volume *vol, uint64_t *file_count, uint64_t *delete_count);
 void swec_ec_volume_close(swec_ec_volume *vol);
 
 /* ---- index files either side of the path (host only, no GPU) ---------------------------------- */

@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cctype>
 #include <cinttypes>
 #include <cstdio>
@@ -481,6 +482,26 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
             if (rd.status != SWEC_OK) continue;
             memcpy(rd.buf + rcv.buf_off, rcv.bufs[size_t(rcv.shard)].data(), rcv.len);
         }
+    }
+    return SWEC_OK;
+}
+
+// FileAndDeleteCount (ec_volume.go:330-349): entries of the sealed .ecx, and distinct journalled ids.
+int swec_ec_volume_counts(swec_ec_volume* v, uint64_t* file_count, uint64_t* delete_count) {
+    if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");
+    std::lock_guard<std::mutex> lock(v->mu);
+    struct stat st;
+    const int64_t now = stat((v->index_base + ".ecj").c_str(), &st) == 0 ? int64_t(st.st_size) : 0;
+    if (now != v->ecj_size_seen) {
+        if (now == 0 || !slurp(v->index_base + ".ecj", &v->ecj)) v->ecj.clear();
+        v->ecj_size_seen = now;
+    }
+    if (file_count) *file_count = uint64_t(v->ecx.size() / 16);
+    if (delete_count) {
+        std::vector<uint64_t> ids;
+        for (size_t off = 0; off + 8 <= v->ecj.size(); off += 8) ids.push_back(be64(reinterpret_cast<const uint8_t*>(v->ecj.data()) + off));
+        std::sort(ids.begin(), ids.end());
+        *delete_count = uint64_t(std::unique(ids.begin(), ids.end()) - ids.begin());
     }
     return SWEC_OK;
 }

@@ -376,6 +376,14 @@ class EcVolume:
 
     DeleteNeedleFromEcx = delete_needle
 
+    def file_and_delete_count(self) -> tuple[int, int]:
+        """FileAndDeleteCount (ec_volume.go:330-349)"""
+        f, d = C.c_uint64(0), C.c_uint64(0)
+        check(lib().swec_ec_volume_counts(self._h, C.byref(f), C.byref(d)))
+        return int(f.value), int(d.value)
+
+    FileAndDeleteCount = file_and_delete_count
+
     def close(self) -> None:
         h, self._h = getattr(self, "_h", None), None
         if h and callable(lib):

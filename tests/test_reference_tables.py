@@ -2,6 +2,8 @@
 the oracle): the expected-shard-size table and the .ecx / .ecj / .idx decode-side cases.
 
   TestCalculateExpectedShardSize              weed/storage/disk_location_ec_shard_size_test.go:7-143
+  TestEcVolumeFileAndDeleteCountInitial / AfterDelete
+                                              weed/storage/erasure_coding/ec_volume_counts_test.go:61-130
   TestHasLiveNeedles_*, TestWriteIdxFileFromEcIndex_*, TestDecodeWithNonEmptyEcj_*, TestDecodeWithEmptyEcj,
   TestDecodeWithNoEcjFile                     weed/storage/erasure_coding/ec_decoder_test.go:13-390
 """
@@ -119,3 +121,33 @@ def test_decode_with_empty_or_missing_ecj(swec, tmp_path, ecj):
     assert open(base + ".ecx", "rb").read() == ecx and ec.HasLiveNeedles(base) is True
     ec.WriteIdxFileFromEcIndex(base)
     assert open(base + ".idx", "rb").read() == ecx
+
+
+def _mount_fixture(ec, tmp_path, ecx, ecj_ids):
+    """writeFixture (ec_volume_counts_test.go:34-57): .ecx, .ecj, an 8-byte .ec00 and an EMPTY .vif"""
+    base = str(tmp_path / "test_1")
+    open(base + ".ecx", "wb").write(ecx)
+    open(base + ".ecj", "wb").write(b"".join(i.to_bytes(8, "big") for i in ecj_ids))
+    open(base + ".ec00", "wb").write(bytes(8))
+    open(base + ".vif", "wb").write(b"")
+    return ec.EcVolume(base, device=-1)
+
+
+def test_ec_volume_file_and_delete_count_initial(swec, tmp_path):
+    ec = swec.erasure_coding
+    ev = _mount_fixture(ec, tmp_path, entry(1, 64, 100) + entry(2, 128, 200) + entry(3, 256, 300), [2, 3])
+    assert ev.FileAndDeleteCount() == (3, 2)
+    ev.close()
+
+
+def test_ec_volume_file_and_delete_count_after_delete(swec, tmp_path):
+    ec = swec.erasure_coding
+    ev = _mount_fixture(ec, tmp_path, entry(1, 64, 100) + entry(2, 128, 200), [])
+    assert ev.FileAndDeleteCount() == (2, 0)
+    ev.DeleteNeedleFromEcx(2)
+    assert ev.FileAndDeleteCount() == (2, 1)
+    ev.DeleteNeedleFromEcx(2)                                            # idempotent
+    assert ev.FileAndDeleteCount() == (2, 1)
+    ev.DeleteNeedleFromEcx(99)                                           # not in the volume
+    assert ev.FileAndDeleteCount() == (2, 1)
+    ev.close()
