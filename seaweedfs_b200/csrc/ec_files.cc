@@ -24,6 +24,7 @@
 #include <functional>
 #include <memory>
 #include <thread>
+#include <time.h>
 
 #include "engine.h"
 
@@ -52,7 +53,8 @@ struct FdSet {
     }
 };
 
-struct ReadOp { int stream, fd; int64_t off; };            // fill stream `stream` of the slot from fd@off
+// fill bytes [dst_off, dst_off+len) of the slot's stream `stream` from fd@off (zero past EOF)
+struct ReadOp { int stream, fd; int64_t off; size_t dst_off, len; };
 struct WriteOp { int stream, fd; int64_t off; };           // drain stream `stream` of the slot to fd@off
 struct Item {
     size_t len = 0;
@@ -142,9 +144,21 @@ class IoPool {
     bool stop_ = false;
 };
 
+// wall-clock breakdown of one pipeline run, printed to stderr as JSON when SWEC_PIPE_STATS is set
+struct PipeStats {
+    double setup = 0, prealloc = 0, wait_slot = 0, read = 0, enqueue = 0, wait_gpu = 0, write = 0, total = 0;
+    int items = 0;
+    static double now() {
+        struct timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        return double(t.tv_sec) + double(t.tv_nsec) * 1e-9;
+    }
+};
+
 // K input streams + R computed streams per slot, pitch = chunk bytes.
 class FilePipeline {
   public:
+    PipeStats stats;
     // verify = true: streams [K, K+R) are the parity bytes read from disk; the computed parity goes to
     // streams [K+R, K+2R) and is only compared on the device (no D2H, no writes).
     FilePipeline(swec_encoder* enc, const Matrix& rows, size_t chunk, bool verify = false)
@@ -152,6 +166,13 @@ class FilePipeline {
     ~FilePipeline() { shutdown(); }
 
     int start() {
+        const double t_start = PipeStats::now();
+        struct SetupTimer {
+            PipeStats& st;
+            double t0;
+            ~SetupTimer() { st.setup += PipeStats::now() - t0; st.total -= 0; }
+        } setup_timer{stats, t_start};
+        t_begin_ = t_start;
         int rc = enc_->ensure_device();
         if (rc) return rc;
         const size_t nslots = env_sz("SWEC_STAGE_SLOTS", 3);
@@ -178,6 +199,7 @@ class FilePipeline {
     // blocking: read the item's inputs, queue the GPU work, hand the slot to the writer
     int submit(Item&& item) {
         Slot* s = nullptr;
+        double t0 = PipeStats::now();
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&] { return !free_.empty() || error_; });
@@ -185,11 +207,15 @@ class FilePipeline {
             s = free_.front();
             free_.pop_front();
         }
+        double t1 = PipeStats::now();
+        stats.wait_slot += t1 - t0;
+        stats.items++;
         const int K = rows_.cols, R = rows_.rows;
         const size_t len = item.len;
         const std::function<int(int)> read_one = [&](int idx) -> int {
             const ReadOp& r = item.reads[size_t(idx)];
-            uint8_t* dst = s->host + size_t(r.stream) * chunk_;
+            uint8_t* dst = s->host + size_t(r.stream) * chunk_ + r.dst_off;
+            const size_t len = r.len;
             size_t got = 0;
             while (got < len) {
                 const ssize_t n = pread(r.fd, dst + got, len - got, off_t(r.off + int64_t(got)));
@@ -209,6 +235,8 @@ class FilePipeline {
             set_last_error(noted_error());
             return set_error(rrc, s);
         }
+        t0 = PipeStats::now();
+        stats.read += t0 - t1;
         if (cudaSetDevice(enc_->device) != cudaSuccess) return set_error(fail(SWEC_ERR_CUDA, "cudaSetDevice"), s);
         cudaError_t e = cudaSuccess;
         const uint8_t* din[SWEC_MAX_SHARDS];
@@ -246,6 +274,7 @@ class FilePipeline {
             inflight_.push_back(s);
         }
         cv_.notify_all();
+        stats.enqueue += PipeStats::now() - t0;
         return SWEC_OK;
     }
 
@@ -256,6 +285,17 @@ class FilePipeline {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return (inflight_.empty() && free_.size() == slots_.size()) || error_; });
         return error_;
+    }
+
+    void report(const char* what) {
+        if (!getenv("SWEC_PIPE_STATS")) return;
+        stats.total = PipeStats::now() - t_begin_;
+        fprintf(stderr,
+                "{\"pipe\": \"%s\", \"items\": %d, \"chunk\": %zu, \"total_s\": %.3f, \"setup_s\": %.3f, \"prealloc_s\": %.3f, "
+                "\"reader\": {\"wait_slot_s\": %.3f, \"read_s\": %.3f, \"enqueue_s\": %.3f}, "
+                "\"writer\": {\"wait_gpu_s\": %.3f, \"write_s\": %.3f}}\n",
+                what, stats.items, chunk_, stats.total, stats.setup, stats.prealloc, stats.wait_slot, stats.read, stats.enqueue,
+                stats.wait_gpu, stats.write);
     }
 
     void shutdown() {
@@ -323,7 +363,10 @@ class FilePipeline {
                 s = inflight_.front();
             }
             int rc = SWEC_OK;
+            const double tw0 = PipeStats::now();
             if (cudaEventSynchronize(s->done) != cudaSuccess) rc = fail(SWEC_ERR_CUDA, "cudaEventSynchronize failed in the shard writer");
+            const double tw1 = PipeStats::now();
+            stats.wait_gpu += tw1 - tw0;   // writer thread only
             if (!rc) {
                 const std::function<int(int)> write_one = [&](int idx) -> int {
                     const WriteOp& w = s->item.writes[size_t(idx)];
@@ -343,6 +386,7 @@ class FilePipeline {
                 };
                 rc = io_->parallel_for(int(s->item.writes.size()), write_one);
                 if (rc) set_last_error(noted_error());
+                stats.write += PipeStats::now() - tw1;
             }
             {
                 std::lock_guard<std::mutex> lk(mu_);
@@ -360,6 +404,7 @@ class FilePipeline {
     swec_encoder* enc_;
     Matrix rows_;
     size_t chunk_;
+    double t_begin_ = 0;
     bool verify_ = false;
     unsigned long long* dev_bad_ = nullptr;
     std::vector<Slot> slots_;
@@ -459,40 +504,57 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
     // zero-fills on fallocate — so the writers fill pages/extents that already exist instead of
     // growing 14 files 8 MiB at a time under the filesystem's allocation lock (best effort).
     if (!getenv("SWEC_NO_FALLOCATE")) {
+        const double tp = PipeStats::now();
         const int64_t shard_size = swec_expected_shard_size(st.st_size, k, large, small);
         if (shard_size > 0)
             pipe.parallel_for(total, [&](int i) -> int {
                 (void)posix_fallocate(outs[size_t(i)], 0, off_t(shard_size));
                 return 0;
             });
+        pipe.stats.prealloc += PipeStats::now() - tp;
     }
 
     int64_t remaining = st.st_size, processed = 0, shard_off = 0;
     const int64_t large_row = large * k, small_row = small * k;
-    auto encode_row = [&](int64_t block) -> int {  // encodeData: one row of k blocks
-        for (int64_t o = 0; o < block; o += int64_t(chunk)) {
+    auto encode_large_row = [&]() -> int {  // encodeData on one row of k large blocks, chunk by chunk
+        for (int64_t o = 0; o < large; o += int64_t(chunk)) {
             Item it;
-            it.len = size_t(std::min<int64_t>(int64_t(chunk), block - o));
-            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + block * i + o});
+            it.len = size_t(std::min<int64_t>(int64_t(chunk), large - o));
+            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + large * i + o, 0, it.len});
             for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off + o});
             const int r = pipe.submit(std::move(it));
             if (r) return r;
         }
-        shard_off += block;
+        shard_off += large;
         return SWEC_OK;
     };
     while (rc == SWEC_OK && remaining >= large_row) {  // ec_encoder.go:304-311
-        rc = encode_row(large);
+        rc = encode_large_row();
         remaining -= large_row;
         processed += large_row;
     }
-    while (rc == SWEC_OK && remaining > 0) {  // ec_encoder.go:312-319
-        rc = encode_row(small);
-        remaining -= small_row;
-        processed += small_row;
+    // Small rows (ec_encoder.go:312-319) are tiny (10 x 1 MiB): many of them share one slot.  Row j of the
+    // batch is one contiguous k*small run of the .dat whose k blocks scatter to offset j*small of the k input
+    // streams, so every shard still receives ONE contiguous write per item.  A default 30,000 MiB volume is
+    // 2 large rows + 952 small ones — a third of its bytes take this path.
+    const int64_t rows_per_item = std::max<int64_t>(1, int64_t(chunk) / small);
+    while (rc == SWEC_OK && remaining > 0) {
+        const int64_t rows_left = (remaining + small_row - 1) / small_row;
+        const int64_t n = std::min(rows_per_item, rows_left);
+        Item it;
+        it.len = size_t(n * small);
+        for (int64_t j = 0; j < n; j++)
+            for (int i = 0; i < k; i++)
+                it.reads.push_back({i, dat, processed + j * small_row + int64_t(i) * small, size_t(j * small), size_t(small)});
+        for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off});
+        rc = pipe.submit(std::move(it));
+        shard_off += n * small;
+        remaining -= n * small_row;
+        processed += n * small_row;
     }
     const int rc2 = pipe.finish();
     if (rc == SWEC_OK) rc = rc2;
+    pipe.report("generate_ec_files");
     const std::string msg = pipe.error_message();
     pipe.shutdown();
     if (rc && !msg.empty()) set_last_error(msg);
@@ -602,7 +664,7 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     for (int64_t o = 0; rc == SWEC_OK && o < todo; o += int64_t(chunk)) {
         Item it;
         it.len = size_t(std::min<int64_t>(int64_t(chunk), todo - o));
-        for (int i = 0; i < k; i++) it.reads.push_back({i, in[size_t(ins[size_t(i)])], o});
+        for (int i = 0; i < k; i++) it.reads.push_back({i, in[size_t(ins[size_t(i)])], o, 0, it.len});
         for (size_t r = 0; r < outs_idx.size(); r++) it.writes.push_back({k + int(r), out[size_t(outs_idx[r])], o});
         rc = pipe.submit(std::move(it));
     }
@@ -666,7 +728,7 @@ int swec_verify_ec_files(const char* base, const char* const* dirs, int ndirs, i
     for (int64_t o = 0; rc == SWEC_OK && o < size; o += int64_t(chunk)) {
         Item it;
         it.len = size_t(std::min<int64_t>(int64_t(chunk), size - o));
-        for (int i = 0; i < total; i++) it.reads.push_back({i, in[size_t(i)], o});
+        for (int i = 0; i < total; i++) it.reads.push_back({i, in[size_t(i)], o, 0, it.len});
         rc = pipe.submit(std::move(it));
     }
     const int rc2 = pipe.finish();
