@@ -48,9 +48,15 @@ def main():
     t[:size].cpu().numpy().tofile(base + ".dat")
     del t
     out = {"dat_bytes": size, "dir": args.dir}
-    ec.write_ec_files(base)                                       # warm-up (pinned slots, context)
+    ec.write_ec_files(base)                                       # warm-up (context, page cache)
     t0 = time.perf_counter()
-    ec.write_ec_files(base)
+    ec.write_ec_files(base)                                       # over the warm-up's shard files: O_TRUNC frees 1.4x the
+    dt = time.perf_counter() - t0                                 # volume in page-cache / tmpfs pages before the first byte
+    out["write_ec_files_over_existing_shards_GBps"] = round(size / dt / 1e9, 2)
+    for i in range(14):
+        os.remove(base + ec.ToExt(i))
+    t0 = time.perf_counter()
+    ec.write_ec_files(base)                                       # what ec.encode does: the shard files do not exist yet
     dt = time.perf_counter() - t0
     out["write_ec_files_GBps"] = round(size / dt / 1e9, 2)
     digests = [sha(base + ec.ToExt(i)) for i in range(14)]

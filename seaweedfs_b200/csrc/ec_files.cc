@@ -469,6 +469,7 @@ extern "C" {
 int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large, int64_t small, int k, int m,
                            int device) {
     if (!base) return fail(SWEC_ERR_INVALID_ARG, "base_file_name is NULL");
+    const double t_call = PipeStats::now();
     // encodeData: "unexpected zero buffer size" / "unexpected block size %d buffer size %d" (ec_encoder.go:204-212)
     if (buffer_size <= 0 || large <= 0 || small <= 0 || large % buffer_size || small % buffer_size)
         return fail(SWEC_ERR_INVALID_ARG, "block sizes must be positive multiples of buffer_size");
@@ -497,6 +498,7 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
     memcpy(rows.v.data(), enc->gen.row(k), rows.v.size());
     const int64_t max_chunk = int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20));
     const size_t chunk = size_t(std::min<int64_t>(max_chunk, std::max(large, small)) + 255) & ~size_t(255);
+    const double t_opened = PipeStats::now();
     FilePipeline pipe(enc, rows, chunk);
     if ((rc = pipe.start())) return rc;
 
@@ -555,8 +557,13 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
     const int rc2 = pipe.finish();
     if (rc == SWEC_OK) rc = rc2;
     pipe.report("generate_ec_files");
+    const double t_piped = PipeStats::now();
     const std::string msg = pipe.error_message();
     pipe.shutdown();
+    if (getenv("SWEC_PIPE_STATS"))
+        fprintf(stderr, "{\"call\": \"generate_ec_files\", \"dat_bytes\": %lld, \"open_and_truncate_s\": %.3f, \"pipeline_s\": %.3f, "
+                        "\"teardown_s\": %.3f}\n",
+                (long long)st.st_size, t_opened - t_call, t_piped - t_opened, PipeStats::now() - t_piped);
     if (rc && !msg.empty()) set_last_error(msg);
     return rc;
 }
