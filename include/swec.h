@@ -67,7 +67,8 @@ const char *swec_version(void);
 const char *swec_strerror(int status);
 const char *swec_last_error(void);            /* thread-local detail of the last failure        */
 int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the driver is absent   */
-/* Stop the library's background compiler thread (idempotent).  Embedders whose runtime tears the
+/* Stop the library's background compiler thread and release the staging rings that file-level calls park
+ * for the next call (idempotent).  Embedders whose runtime tears the
  * process down in stages (CPython's Py_Finalize) call this from their own exit hook; the library
  * also registers it with atexit().  Everything keeps working afterwards, without background JIT. */
 void swec_shutdown(void);

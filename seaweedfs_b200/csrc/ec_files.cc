@@ -144,6 +144,37 @@ class IoPool {
     bool stop_ = false;
 };
 
+// Staging rings outlive a call: pinning (mmap + mbind + cudaHostRegister) and un-pinning 3 x 14 x 8 MiB costs
+// 0.1-2 s per call (profiles/r01z_files_*), as much as the pipeline itself spends on an 8 GiB volume.  A volume
+// server encodes volume after volume, so finished pipelines park their ring here (per device and size, a few at
+// most) and the next call picks it up.  swec_shutdown() releases them.
+struct SlotSet {
+    int device = -1;
+    size_t bytes_per_slot = 0;
+    std::vector<Slot> slots;
+};
+std::mutex& slotset_mu() {
+    static std::mutex* m = new std::mutex;
+    return *m;
+}
+std::vector<SlotSet>& slotset_cache() {
+    static std::vector<SlotSet>* c = new std::vector<SlotSet>;  // leaked on purpose: no CUDA calls in static destructors
+    return *c;
+}
+constexpr size_t kMaxCachedSlotSets = 4;
+
+void free_slots(int device, std::vector<Slot>& slots) {
+    if (cudaSetDevice(device) != cudaSuccess) cudaGetLastError();
+    for (auto& s : slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.host) pinned_free(s.host);
+        if (s.dev) cudaFree(s.dev);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    slots.clear();
+}
+
 // wall-clock breakdown of one pipeline run, printed to stderr as JSON when SWEC_PIPE_STATS is set
 struct PipeStats {
     double setup = 0, prealloc = 0, wait_slot = 0, read = 0, enqueue = 0, wait_gpu = 0, write = 0, total = 0;
@@ -181,13 +212,34 @@ class FilePipeline {
             SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev_bad_), sizeof(unsigned long long) * size_t(rows_.rows)));
             SWEC_CUDA(cudaMemset(dev_bad_, 0, sizeof(unsigned long long) * size_t(rows_.rows)));
         }
-        slots_.resize(nslots);
+        slot_bytes_ = streams * chunk_;
+        {
+            std::lock_guard<std::mutex> lk(slotset_mu());
+            auto& cache = slotset_cache();
+            for (size_t i = 0; i < cache.size(); i++)
+                if (cache[i].device == enc_->device && cache[i].bytes_per_slot == slot_bytes_ && cache[i].slots.size() == nslots) {
+                    slots_ = std::move(cache[i].slots);
+                    cache.erase(cache.begin() + long(i));
+                    break;
+                }
+        }
+        if (slots_.empty()) {
+            slots_.resize(nslots);
+            for (auto& s : slots_) {
+                s.host = static_cast<uint8_t*>(pinned_alloc(enc_->device, slot_bytes_));
+                cudaError_t e = s.host ? cudaSuccess : cudaErrorMemoryAllocation;
+                if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s.dev), slot_bytes_);
+                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+                if (e != cudaSuccess) {
+                    const int frc = s.host ? cuda_fail(e, "allocating the staging ring") : fail(SWEC_ERR_NOMEM, "cannot allocate pinned staging memory");
+                    free_slots(enc_->device, slots_);
+                    return frc;
+                }
+            }
+        }
         for (auto& s : slots_) {
-            s.host = static_cast<uint8_t*>(pinned_alloc(enc_->device, streams * chunk_));
-            if (!s.host) return fail(SWEC_ERR_NOMEM, "cannot allocate pinned staging memory");
-            SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk_));
-            SWEC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            SWEC_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            s.item = Item{};
             free_.push_back(&s);
         }
         io_.reset(new IoPool(env_sz("SWEC_IO_THREADS", std::min<size_t>(16, std::max<size_t>(4, std::thread::hardware_concurrency() / 4)))));
@@ -308,14 +360,27 @@ class FilePipeline {
         if (writer_.joinable()) writer_.join();
         io_.reset();
         cudaSetDevice(enc_->device);
-        for (auto& s : slots_) {
-            if (s.stream) cudaStreamSynchronize(s.stream);
-            if (s.host) pinned_free(s.host);
-            if (s.dev) cudaFree(s.dev);
-            if (s.done) cudaEventDestroy(s.done);
-            if (s.stream) cudaStreamDestroy(s.stream);
+        bool healthy = error_ == 0;
+        for (auto& s : slots_)
+            if (s.stream && cudaStreamSynchronize(s.stream) != cudaSuccess) {
+                cudaGetLastError();
+                healthy = false;
+            }
+        free_.clear();
+        inflight_.clear();
+        if (healthy && !slots_.empty() && !getenv("SWEC_NO_RING_CACHE")) {  // park the ring for the next call
+            std::lock_guard<std::mutex> lk(slotset_mu());
+            auto& cache = slotset_cache();
+            if (cache.size() < kMaxCachedSlotSets) {
+                SlotSet set;
+                set.device = enc_->device;
+                set.bytes_per_slot = slot_bytes_;
+                set.slots = std::move(slots_);
+                cache.push_back(std::move(set));
+                slots_.clear();
+            }
         }
-        slots_.clear();
+        if (!slots_.empty()) free_slots(enc_->device, slots_);
         if (dev_bad_) cudaFree(dev_bad_);
         dev_bad_ = nullptr;
         started_ = false;
@@ -408,6 +473,7 @@ class FilePipeline {
     bool verify_ = false;
     unsigned long long* dev_bad_ = nullptr;
     std::vector<Slot> slots_;
+    size_t slot_bytes_ = 0;
     std::deque<Slot*> free_, inflight_;
     std::mutex mu_;
     std::condition_variable cv_;
@@ -460,6 +526,16 @@ bool file_exists(const std::string& p) {
 }
 
 }  // namespace
+
+void file_pipeline_trim() {  // swec_shutdown(): release parked staging rings
+    std::vector<SlotSet> sets;
+    {
+        std::lock_guard<std::mutex> lk(slotset_mu());
+        sets.swap(slotset_cache());
+    }
+    for (auto& set : sets) free_slots(set.device, set.slots);
+}
+
 }  // namespace swec
 
 using namespace swec;

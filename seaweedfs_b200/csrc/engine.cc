@@ -629,7 +629,10 @@ int swec_device_count(int* count) {
 
 uint64_t swec_kernel_launches(void) { return g_kernel_launches.load(); }
 
-void swec_shutdown(void) { jit_shutdown(); }
+void swec_shutdown(void) {
+    jit_shutdown();
+    file_pipeline_trim();
+}
 
 int swec_debug_jit_compile(int r, int k, const uint8_t* rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
     if (r <= 0 || k <= 0 || k > SWEC_MAX_INPUTS || !rows) return fail(SWEC_ERR_INVALID_ARG, "bad matrix");

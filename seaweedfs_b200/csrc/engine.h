@@ -38,6 +38,7 @@ int device_numa_node(int device);
 
 // ecShardConfig.{dataShards,parityShards} of a .vif file (ec_files.cc); false when absent/unreadable
 bool read_vif_ratio(const std::string& path, int* ds, int* ps);
+void file_pipeline_trim();  // ec_files.cc: release staging rings parked between file-level calls
 
 // device-resident multiply tables of one R×K matrix (R ≤ 4)
 struct DeviceTables {
