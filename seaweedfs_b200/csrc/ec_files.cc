@@ -144,6 +144,8 @@ class IoPool {
     bool stop_ = false;
 };
 
+// ---- end of IoPool (tests/test_iopool.py compiles the class above on its own under the sanitizers)
+
 // Staging rings outlive a call: pinning (mmap + mbind + cudaHostRegister) and un-pinning 3 x 14 x 8 MiB costs
 // 0.1-2 s per call (profiles/r01z_files_*), as much as the pipeline itself spends on an 8 GiB volume.  A volume
 // server encodes volume after volume, so finished pipelines park their ring here (per device and size, a few at

@@ -35,7 +35,7 @@ int main() {
 @pytest.mark.parametrize("sanitizer", ["thread", "address"])
 def test_iopool_under_sanitizers(tmp_path, sanitizer):
     src = open(os.path.join(ROOT, "seaweedfs_b200", "csrc", "ec_files.cc")).read()
-    cls = src[src.index("class IoPool {"):src.index("// K input streams + R computed streams per slot")]
+    cls = src[src.index("class IoPool {"):src.index("// ---- end of IoPool")]
     head = "\n".join(f"#include <{h}>" for h in ("algorithm", "atomic", "condition_variable", "cstdio", "deque",
                                                   "functional", "mutex", "thread", "vector"))
     (tmp_path / "t.cc").write_text(head + "\n" + cls + MAIN)
