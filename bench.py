@@ -354,6 +354,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reconstruct", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-files", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "swec" else args.warmup
     if args.impl == "reference":
@@ -584,6 +585,23 @@ def main():
             L.swec_free_pinned(raw)
     barrier()
 
+    # ---- file level (BASELINE configs[4] in miniature), rank 0 at N=1: WriteEcFiles / RebuildEcFiles on an 8 GiB
+    # .dat in RAM-backed storage next to the reference-shaped serial walk with SIMD Encode; shards byte-compared
+    files = None
+    if rank == 0 and world == 1 and not args.no_files:
+        try:
+            import shutil
+            import types
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_files
+            fdir = next((d_ for d_ in ("/dev/shm", "/tmp") if os.path.isdir(d_) and shutil.disk_usage(d_).free > (28 << 30)), None)
+            if fdir:
+                del dat, par
+                torch.cuda.empty_cache()
+                files = bench_files.run(types.SimpleNamespace(dir=fdir, gib=8.0, cpu_gib=1.0))
+        except Exception as ex:                                  # noqa: BLE001
+            files = {"error": repr(ex)}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         ms_step = ms_max / args.steps
@@ -608,7 +626,7 @@ def main():
                          "peak_source": peak_src,
                          "kernel": "rs10x4_encode_blocked", "algorithmic_bytes_per_launch": int(algo_bytes),
                          "kernel_ms": round(kernel_ms, 4)},
-            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "reconstruct": recon, "sustained": sustained,
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "reconstruct": recon, "sustained": sustained, "file_level": files,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

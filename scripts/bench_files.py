@@ -31,7 +31,11 @@ def main():
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--gib", type=float, default=4.0)
     ap.add_argument("--cpu-gib", type=float, default=1.0)
-    args = ap.parse_args()
+    print(json.dumps(run(ap.parse_args())))
+
+
+def run(args):
+    """args: .dir, .gib, .cpu_gib → result dict (also called by bench.py's file-level leg)"""
     import numpy as np
     import torch
     import seaweedfs_b200
@@ -91,7 +95,7 @@ def main():
     for f in os.listdir(d):
         os.remove(os.path.join(d, f))
     os.rmdir(d)
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
