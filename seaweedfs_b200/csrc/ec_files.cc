@@ -214,7 +214,9 @@ class FilePipeline {
             SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev_bad_), sizeof(unsigned long long) * size_t(rows_.rows)));
             SWEC_CUDA(cudaMemset(dev_bad_, 0, sizeof(unsigned long long) * size_t(rows_.rows)));
         }
-        slot_bytes_ = streams * chunk_;
+        // one size for every kind of pipeline of this code on this device (generate: k+m streams, rebuild: k + missing,
+        // verify: k+2m), so that a parked ring fits whichever call comes next
+        slot_bytes_ = std::max(streams, size_t(enc_->k + 2 * enc_->m)) * chunk_;
         {
             std::lock_guard<std::mutex> lk(slotset_mu());
             auto& cache = slotset_cache();
