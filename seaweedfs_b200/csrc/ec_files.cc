@@ -13,6 +13,7 @@
 #include <fcntl.h>
 #include <libgen.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -43,6 +44,15 @@ std::string shard_ext(int idx) {  // ToExt, ec_encoder.go:106-108
     char b[16];
     snprintf(b, sizeof b, ".ec%02d", idx);
     return b;
+}
+
+// posix_fallocate pays on disk filesystems (extents reserved once instead of 14 files growing 8 MiB at a time) and
+// costs on tmpfs, where it zero-fills every page that the writers overwrite a moment later.
+bool worth_preallocating(int fd) {
+    if (getenv("SWEC_NO_FALLOCATE")) return false;
+    struct statfs fs;
+    if (fstatfs(fd, &fs) != 0) return true;
+    return fs.f_type != 0x01021994 /* TMPFS_MAGIC */ && fs.f_type != 0x858458f6 /* RAMFS_MAGIC */;
 }
 
 struct FdSet {
@@ -206,6 +216,7 @@ class FilePipeline {
             ~SetupTimer() { st.setup += PipeStats::now() - t0; st.total -= 0; }
         } setup_timer{stats, t_start};
         t_begin_ = t_start;
+        enc_->never_wait_for_jit = !getenv("SWEC_FILE_JIT_WAIT");
         int rc = enc_->ensure_device();
         if (rc) return rc;
         const size_t nslots = env_sz("SWEC_STAGE_SLOTS", 3);
@@ -585,7 +596,7 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
     // The final shard size is known up front: reserve it — one I/O thread per file, because tmpfs
     // zero-fills on fallocate — so the writers fill pages/extents that already exist instead of
     // growing 14 files 8 MiB at a time under the filesystem's allocation lock (best effort).
-    if (!getenv("SWEC_NO_FALLOCATE")) {
+    if (worth_preallocating(outs[0])) {
         const double tp = PipeStats::now();
         const int64_t shard_size = swec_expected_shard_size(st.st_size, k, large, small);
         if (shard_size > 0)
@@ -743,7 +754,7 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     const size_t chunk = std::max<size_t>(256, (size_t(std::min<int64_t>(int64_t(env_sz("SWEC_FILE_CHUNK", size_t(8) << 20)), std::max<int64_t>(todo, 1))) + 255) & ~size_t(255));
     FilePipeline pipe(enc, fused, chunk);
     if ((rc = pipe.start())) return rc;
-    if (!getenv("SWEC_NO_FALLOCATE") && todo > 0)
+    if (todo > 0 && worth_preallocating(out[size_t(outs_idx[0])]))
         pipe.parallel_for(int(outs_idx.size()), [&](int r) -> int {
             (void)posix_fallocate(out[size_t(outs_idx[size_t(r)])], 0, off_t(todo));
             return 0;

@@ -298,8 +298,8 @@ int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8
             const size_t jit_min = size_t(g_opt_jit_min_bytes.load());
             std::shared_ptr<JitKernel> jk;
             if (R <= SWEC_MAX_OUTPUTS && g_opt_jit_enabled.load() && jit_available()) {
-                const bool wait = size_t(K) * n >= jit_min || layout.blocked;
-                const int rc = jit_get(this, rows, &jk, wait);
+                const bool wait = (size_t(K) * n >= jit_min && !never_wait_for_jit) || layout.blocked;
+                const int rc = jit_get(this, rows, &jk, wait, /*hot=*/never_wait_for_jit);
                 if (rc != SWEC_OK && getenv("SWEC_JIT_STRICT")) return rc;
             }
             if (jk) {

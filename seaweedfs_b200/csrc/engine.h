@@ -72,6 +72,9 @@ struct swec_encoder_impl {
     std::map<std::vector<uint8_t>, std::shared_ptr<JitKernel>> jit;  // same key
     std::vector<StagingSlot> slots;
     size_t slot_chunk = 0;
+    // file pipelines never stall on a kernel compile: a cold matrix is served by the table kernel (100x faster
+    // than the I/O around it) while the specialised kernel is built in the background and picked up when ready
+    bool never_wait_for_jit = false;
     uint8_t* tail_scratch = nullptr;  // k*small zero-padded last row
     size_t tail_scratch_bytes = 0;
 
@@ -88,7 +91,7 @@ struct swec_encoder_impl {
 // true when SWEC_NO_JIT is unset and NVRTC could be loaded
 bool jit_available();
 // Specialised Horner kernel for `rows` on the current device (compiled once per matrix/process).
-int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait = true);
+int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait = true, bool hot = false);
 int jit_debug_compile(const Matrix& rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops);
 void jit_shutdown();  // stop the background compiler (idempotent); inline compiles keep working
 bool jit_cached(swec_encoder_impl* enc, const Matrix& rows);

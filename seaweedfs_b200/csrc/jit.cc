@@ -212,7 +212,7 @@ std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unr
 // Long streams (wait = true) compile inline on the calling thread — ≈0.3 s, amortised.  Short ones never
 // block: they are served by the table kernel, and a matrix that keeps coming back (degraded reads
 // behind one dead server) is compiled once by the background worker and picked up when ready.
-int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait) {
+int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait, bool hot) {
     const int threads = int(g_opt_enc_threads.load()), unroll = int(g_opt_enc_unroll.load());
     const int variant = effective_xt_variant();  // boost-clock or low-power step, by the device's recent load
     const std::vector<uint8_t> key = jit_key(rows, threads, unroll, variant);
@@ -233,7 +233,7 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
             return e.kernel ? SWEC_OK : SWEC_ERR_JIT;
         }
         if (!wait) {
-            if (e.state == JitEntry::kCold && ++e.uses >= kHotUses && g.queue.size() < kMaxQueued && !g.stop) {
+            if (e.state == JitEntry::kCold && (++e.uses >= kHotUses || hot) && g.queue.size() < kMaxQueued && !g.stop) {
                 int dev = 0;
                 cudaGetDevice(&dev);
                 e.state = JitEntry::kQueued;
