@@ -863,35 +863,80 @@ int swec_write_dat_file(const char* base, int64_t dat_size, const char* const* s
         fds.fds.push_back(fd);
         in.push_back(fd);
     }
-    std::vector<uint8_t> buf(size_t(4) << 20);
+    // The copy plan of the reference's two loops (ec_decoder.go:200-219) — shard s is read sequentially, the .dat is
+    // written sequentially — as independent (shard offset → .dat offset) pieces, executed in parallel: every piece
+    // has explicit offsets on both sides, so the order of execution cannot change the bytes.
+    struct Piece { int shard; int64_t shard_off, dat_off, len; };
+    std::vector<Piece> pieces;
+    const int64_t max_piece = int64_t(8) << 20;
     std::vector<int64_t> pos(static_cast<size_t>(k), 0);
-    int64_t out = 0;
-    auto copy = [&](int shard, int64_t n) -> int {  // io.CopyN
-        while (n > 0) {
-            const size_t want = size_t(std::min<int64_t>(n, int64_t(buf.size())));
-            const ssize_t got = pread(in[size_t(shard)], buf.data(), want, off_t(pos[size_t(shard)]));
-            if (got <= 0) return fail(SWEC_ERR_IO, "short read copying shard " + std::to_string(shard));
-            if (pwrite(dat, buf.data(), size_t(got), off_t(out)) != got) return io_fail("write .dat");
-            pos[size_t(shard)] += got;
-            out += got;
-            n -= got;
+    int64_t out = 0, remaining = dat_size;
+    auto plan = [&](int shard, int64_t n) {  // io.CopyN(datFile, inputFiles[shard], n)
+        for (int64_t o = 0; o < n; o += max_piece)
+            pieces.push_back({shard, pos[size_t(shard)] + o, out + o, std::min(max_piece, n - o)});
+        pos[size_t(shard)] += n;
+        out += n;
+    };
+    while (remaining >= int64_t(k) * large)
+        for (int s = 0; s < k; s++) {
+            plan(s, large);
+            remaining -= large;
+        }
+    while (remaining > 0)
+        for (int s = 0; s < k; s++) {
+            const int64_t n = std::min(remaining, small);
+            plan(s, n);
+            remaining -= n;
+        }
+    // a shard shorter than the plan needs is the reference's "copy … block" error: check before writing anything
+    for (int s2 = 0; s2 < k; s2++) {
+        struct stat st;
+        if (fstat(in[size_t(s2)], &st) != 0) return io_fail("fstat shard");
+        if (st.st_size < pos[size_t(s2)]) return fail(SWEC_ERR_IO, "short read copying shard " + std::to_string(s2));
+    }
+    if (ftruncate(dat, off_t(dat_size)) != 0) return io_fail("size .dat");
+    IoPool pool(env_sz("SWEC_IO_THREADS", std::min<size_t>(16, std::max<size_t>(4, std::thread::hardware_concurrency() / 4))));
+    std::mutex err_mu;
+    std::string err_text;
+    const std::function<int(int)> copy_piece = [&](int idx) -> int {
+        const Piece& pc = pieces[size_t(idx)];
+        int64_t done = 0;
+        // kernel-side copy first (no user-space bounce; shares extents where the filesystem can) …
+        while (done < pc.len) {
+            off64_t oi = pc.shard_off + done, oo = pc.dat_off + done;
+            const ssize_t n = copy_file_range(in[size_t(pc.shard)], &oi, dat, &oo, size_t(pc.len - done), 0);
+            if (n <= 0) break;  // unsupported combination, or EOF: the read/write loop below decides
+            done += n;
+        }
+        // … plain pread/pwrite for whatever is left
+        std::vector<uint8_t> buf;
+        while (done < pc.len) {
+            if (buf.empty()) buf.resize(size_t(std::min<int64_t>(pc.len, int64_t(4) << 20)));
+            const size_t want = size_t(std::min<int64_t>(pc.len - done, int64_t(buf.size())));
+            const ssize_t got = pread(in[size_t(pc.shard)], buf.data(), want, off_t(pc.shard_off + done));
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (err_text.empty()) err_text = "short read copying shard " + std::to_string(pc.shard);
+                return SWEC_ERR_IO;
+            }
+            ssize_t put = 0;
+            while (put < got) {
+                const ssize_t w = pwrite(dat, buf.data() + put, size_t(got - put), off_t(pc.dat_off + done + put));
+                if (w < 0 && errno == EINTR) continue;
+                if (w <= 0) {
+                    std::lock_guard<std::mutex> lk(err_mu);
+                    if (err_text.empty()) err_text = std::string("write .dat: ") + strerror(errno);
+                    return SWEC_ERR_IO;
+                }
+                put += w;
+            }
+            done += got;
         }
         return SWEC_OK;
     };
-    int64_t remaining = dat_size;
-    while (remaining >= int64_t(k) * large)  // ec_decoder.go:200-208
-        for (int s = 0; s < k; s++) {
-            const int rc = copy(s, large);
-            if (rc) return rc;
-            remaining -= large;
-        }
-    while (remaining > 0)  // ec_decoder.go:210-219
-        for (int s = 0; s < k; s++) {
-            const int64_t n = std::min(remaining, small);
-            const int rc = copy(s, n);
-            if (rc) return rc;
-            remaining -= n;
-        }
+    const int rc = pool.parallel_for(int(pieces.size()), copy_piece);
+    if (rc) return fail(rc, err_text);
     return SWEC_OK;
 }
 
