@@ -258,7 +258,19 @@ struct swec_ec_volume {
     std::string index_base;
     std::vector<int> shard_fd;  // total entries, -1 = not local
     std::string ecx, ecj;
+    std::vector<uint64_t> deleted;  // ids of .ecj, sorted and unique: the reference's in-memory deletedNeedles set
     int64_t ecj_size_seen = -1;
+    void index_journal() {
+        deleted.clear();
+        for (size_t off = 0; off + 8 <= ecj.size(); off += 8) {
+            uint64_t v = 0;
+            for (int i = 0; i < 8; i++) v = (v << 8) | uint8_t(ecj[off + size_t(i)]);
+            deleted.push_back(v);
+        }
+        std::sort(deleted.begin(), deleted.end());
+        deleted.erase(std::unique(deleted.begin(), deleted.end()), deleted.end());
+    }
+    void refresh_journal(bool force = false);
     swec_encoder* enc = nullptr;  // created on the first recovery, keeps its staging ring and kernels
     ~swec_ec_volume() {
         for (int fd : shard_fd)
@@ -266,6 +278,17 @@ struct swec_ec_volume {
         if (enc) swec_encoder_free(enc);
     }
 };
+
+void swec_ec_volume::refresh_journal(bool force) {
+    // the deletion journal grows while the volume is mounted (DeleteNeedleFromEcx appends to .ecj): pick up new
+    // entries when the file size moved — the reference keeps the same set in memory (ec_volume.go:351-384)
+    struct stat st;
+    const int64_t now = stat((index_base + ".ecj").c_str(), &st) == 0 ? int64_t(st.st_size) : 0;
+    if (!force && now == ecj_size_seen) return;
+    if (now == 0 || !swec::slurp(index_base + ".ecj", &ecj)) ecj.clear();
+    ecj_size_seen = now;
+    index_journal();
+}
 
 extern "C" {
 
@@ -339,23 +362,10 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
     const int k = v->k, total = v->k + v->m, version = v->version;
     const int64_t large = int64_t(1) << 30, small = int64_t(1) << 20;
 
-    // the deletion journal grows while the volume is mounted (DeleteNeedleFromEcx appends to .ecj): pick up
-    // new entries when the file size moved — the reference keeps the same set in memory (ec_volume.go:351-384)
-    {
-        struct stat st;
-        const int64_t now = stat((v->index_base + ".ecj").c_str(), &st) == 0 ? int64_t(st.st_size) : 0;
-        if (now != v->ecj_size_seen) {
-            if (now == 0 || !slurp(v->index_base + ".ecj", &v->ecj)) v->ecj.clear();
-            v->ecj_size_seen = now;
-        }
-    }
+    v->refresh_journal();
     const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
     const int64_t entries = int64_t(v->ecx.size()) / 16;
-    auto journalled = [&](uint64_t id) {
-        for (size_t off = 0; off + 8 <= v->ecj.size(); off += 8)
-            if (be64(reinterpret_cast<const uint8_t*>(v->ecj.data()) + off) == id) return true;
-        return false;
-    };
+    auto journalled = [&](uint64_t id) { return std::binary_search(v->deleted.begin(), v->deleted.end(), id); };
 
     // ---- pass 1: locate every needle, read what is local, collect what must be recovered
     struct Recover {
@@ -407,8 +417,8 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
             rd.status = SWEC_ERR_INVALID_ARG;
             continue;
         }
-        swec_interval ivs[64];
-        const int niv = swec_locate_data(large, small, v->shard_dat_size, offset, want, k, ivs, 64);
+        std::vector<swec_interval> ivs(size_t(want / small) + 4);  // a record crosses at most size/1 MiB + 2 blocks
+        const int niv = swec_locate_data(large, small, v->shard_dat_size, offset, want, k, ivs.data(), int(ivs.size()));
         if (niv < 0) {
             rd.status = niv;
             continue;
@@ -490,19 +500,9 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
 int swec_ec_volume_counts(swec_ec_volume* v, uint64_t* file_count, uint64_t* delete_count) {
     if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");
     std::lock_guard<std::mutex> lock(v->mu);
-    struct stat st;
-    const int64_t now = stat((v->index_base + ".ecj").c_str(), &st) == 0 ? int64_t(st.st_size) : 0;
-    if (now != v->ecj_size_seen) {
-        if (now == 0 || !slurp(v->index_base + ".ecj", &v->ecj)) v->ecj.clear();
-        v->ecj_size_seen = now;
-    }
+    v->refresh_journal();
     if (file_count) *file_count = uint64_t(v->ecx.size() / 16);
-    if (delete_count) {
-        std::vector<uint64_t> ids;
-        for (size_t off = 0; off + 8 <= v->ecj.size(); off += 8) ids.push_back(be64(reinterpret_cast<const uint8_t*>(v->ecj.data()) + off));
-        std::sort(ids.begin(), ids.end());
-        *delete_count = uint64_t(std::unique(ids.begin(), ids.end()) - ids.begin());
-    }
+    if (delete_count) *delete_count = uint64_t(v->deleted.size());
     return SWEC_OK;
 }
 
@@ -546,6 +546,7 @@ int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
             close(fd);
             v->ecj = cur;
             v->ecj_size_seen = st.st_size;
+            v->index_journal();
             return SWEC_OK;
         }
     uint8_t b[8];
@@ -561,6 +562,7 @@ int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
     cur.append(reinterpret_cast<const char*>(b), 8);
     v->ecj = cur;
     v->ecj_size_seen = st.st_size + 8;
+    v->index_journal();
     return SWEC_OK;
 }
 
