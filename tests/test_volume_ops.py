@@ -405,3 +405,20 @@ def test_volume_generate_keeps_ratio_of_existing_vif(cuda, swec, oracle, tmp_pat
     json.dump({"version": 3, "ecShardConfig": {"dataShards": 30, "parityShards": 9}}, open(base + ".vif", "w"))
     ec.VolumeEcShardsGenerate(base)
     assert os.path.exists(base + ec.ToExt(13)) and read_vif(base + ".vif")["ds"] == 10
+
+
+def test_read_ec_needle_spanning_many_blocks(swec, oracle, tmp_path):
+    """A 66 MiB record crosses 67 one-MiB blocks on all ten data shards: the interval list grows with the record."""
+    ec = swec.erasure_coding
+    rng = np.random.default_rng(3)
+    size = 66 * MIB + 12345
+    fixed = 16 + size + 4 + 8
+    actual = fixed + (8 - fixed % 8)
+    dat = np.concatenate([np.array([3, 0, 0, 0, 0, 0, 0, 0], dtype=np.uint8), rng.integers(0, 256, actual + 4096, dtype=np.uint8)])
+    idx = rn._entry(77, 1, size)
+    base, _ = lay_down_ec_volume(oracle, tmp_path, dat, idx)
+    json.dump({"version": 3, "datFileSize": str(len(dat)), "ecShardConfig": {"dataShards": 10, "parityShards": 4}},
+              open(base + ".vif", "w"))
+    r = ec.ReadEcShardNeedles(base, [77], device=-1)[0]
+    want = expected_record(dat, 8, size)
+    assert r["status"] == "SWEC_OK" and r["n_bytes"] == len(want) and (r["bytes"] == want).all()
