@@ -1,5 +1,6 @@
 """Threading contract of the C ABI (include/swec.h): concurrent callers on separate encoder handles
 and on one shared handle, like Go goroutines running several volumes at once (weed/shell/common.go:11)."""
+import os
 import threading
 
 import numpy as np
@@ -118,3 +119,44 @@ def test_one_call_split_over_several_handles(cuda, swec, oracle, n):
     grp.reconstruct(holes, data_only=True)
     assert (holes[4] == shards[4]).all() and holes[13] is None
     grp.close()
+
+
+def test_concurrent_file_level_calls_share_parked_rings(cuda, swec, oracle, tmp_path):
+    """Several volumes encoded and rebuilt at once from different OS threads (the shell's ec.encode runs up to ten,
+    weed/shell/common.go:11), twice over, so that later calls pick up staging rings parked by earlier ones while
+    others are still running.  Every shard file equals the oracle's."""
+    ec = swec.erasure_coding
+    rng = np.random.default_rng(9)
+    vols = []
+    for v in range(4):
+        size = int(rng.integers(3, 12)) * (1 << 20) + int(rng.integers(0, 4096))
+        dat = rng.integers(0, 256, size, dtype=np.uint8)
+        base = str(tmp_path / f"v{v}")
+        dat.tofile(base + ".dat")
+        vols.append((base, oracle.encode_dat_image(dat)))
+    errors = []
+
+    def worker(v):
+        try:
+            base, want = vols[v]
+            for _ in range(2):
+                ec.write_ec_files(base)
+                for i in range(14):
+                    assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all(), (v, i)
+                lost = [(v + j * 3) % 14 for j in range(1 + v % 4)]
+                for i in set(lost):
+                    os.remove(base + ec.ToExt(i))
+                assert ec.rebuild_ec_files(base) == sorted(set(lost))
+                for i in range(14):
+                    assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all(), (v, i, "rebuilt")
+                ok, bad = ec.verify_ec_files(base)
+                assert ok and not any(bad)
+        except Exception as ex:  # noqa: BLE001
+            errors.append((v, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(v,)) for v in range(len(vols))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
