@@ -160,3 +160,37 @@ def test_concurrent_file_level_calls_share_parked_rings(cuda, swec, oracle, tmp_
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_file_pipeline_write_error_surfaces_and_does_not_hang(cuda, swec, tmp_path):
+    """A write that fails in the middle of a volume (disk full / file-size limit) must come back as SWEC_ERR_IO with
+    the errno text — from whichever I/O thread hit it — and leave the pipeline shut down, not hung; the next call on
+    the same device works (the ring of a failed run is not parked).  Run in a child process: RLIMIT_FSIZE."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = textwrap.dedent(f"""
+        import os, resource, signal, sys
+        sys.path.insert(0, {root!r})
+        import numpy as np
+        import seaweedfs_b200
+        from seaweedfs_b200 import erasure_coding as ec
+        base = os.path.join({str(tmp_path)!r}, "5")
+        np.random.default_rng(0).integers(0, 256, 60 << 20, dtype=np.uint8).tofile(base + ".dat")
+        signal.signal(signal.SIGXFSZ, signal.SIG_IGN)             # EFBIG instead of a fatal signal
+        resource.setrlimit(resource.RLIMIT_FSIZE, (3 << 20, resource.RLIM_INFINITY))
+        try:
+            ec.write_ec_files(base)
+            print("NO ERROR")
+        except seaweedfs_b200.SwecError as e:
+            print("ERR", e.name, str(e))
+        resource.setrlimit(resource.RLIMIT_FSIZE, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+        for i in range(14):
+            os.remove(base + ec.ToExt(i))
+        ec.write_ec_files(base)                                   # the engine is healthy afterwards
+        print("RETRY OK", os.path.getsize(base + ".ec13"))
+    """)
+    r = subprocess.run([sys.executable, "-c", child], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert "ERR SWEC_ERR_IO" in r.stdout and "pwrite" in r.stdout, r.stdout[-2000:]
+    assert "RETRY OK 6291456" in r.stdout, r.stdout[-2000:]
