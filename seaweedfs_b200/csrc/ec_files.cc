@@ -609,22 +609,27 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
 
     int64_t remaining = st.st_size, processed = 0, shard_off = 0;
     const int64_t large_row = large * k, small_row = small * k;
-    auto encode_large_row = [&]() -> int {  // encodeData on one row of k large blocks, chunk by chunk
-        for (int64_t o = 0; o < large; o += int64_t(chunk)) {
+    auto encode_row = [&](int64_t block) -> int {  // encodeData on one row of k blocks, chunk by chunk
+        for (int64_t o = 0; o < block; o += int64_t(chunk)) {
             Item it;
-            it.len = size_t(std::min<int64_t>(int64_t(chunk), large - o));
-            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + large * i + o, 0, it.len});
+            it.len = size_t(std::min<int64_t>(int64_t(chunk), block - o));
+            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + block * i + o, 0, it.len});
             for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off + o});
             const int r = pipe.submit(std::move(it));
             if (r) return r;
         }
-        shard_off += large;
+        shard_off += block;
         return SWEC_OK;
     };
     while (rc == SWEC_OK && remaining >= large_row) {  // ec_encoder.go:304-311
-        rc = encode_large_row();
+        rc = encode_row(large);
         remaining -= large_row;
         processed += large_row;
+    }
+    while (rc == SWEC_OK && remaining > 0 && small > int64_t(chunk)) {  // small blocks bigger than a slot: row by row
+        rc = encode_row(small);
+        remaining -= small_row;
+        processed += small_row;
     }
     // Small rows (ec_encoder.go:312-319) are tiny (10 x 1 MiB): many of them share one slot.  Row j of the
     // batch is one contiguous k*small run of the .dat whose k blocks scatter to offset j*small of the k input

@@ -211,3 +211,22 @@ def test_calculate_expected_shard_size_with_real_encoding(cuda, swec, oracle, tm
     base, shards = encode_files(ec, oracle, tmp_path, dat, "edge", large=1 << 30, small=1 << 20, buffer=256 * 1024)
     want = ec.expected_shard_size(dat_size)
     assert all(os.path.getsize(base + ec.ToExt(i)) == want for i in range(14))
+
+
+@pytest.mark.parametrize("large,small,dat_size", [(32 << 20, 16 << 20, (330 << 20) + 12345),     # small block > the 8 MiB slot
+                                                  (1 << 20, 1 << 20, (25 << 20) + 1),             # large == small
+                                                  (3 << 20, 1 << 20, 10 * (3 << 20) + 10 * (1 << 20) * 9 + 5)])  # 1 large + 10 small rows
+def test_generate_ec_files_unusual_block_sizes(cuda, swec, oracle, tmp_path, large, small, dat_size):
+    """generateEcFiles takes its block sizes as arguments (ec_encoder.go:110): the row batching of the file
+    pipeline must hold for small blocks larger than a staging slot, equal block sizes and more small rows than
+    fit one slot."""
+    ec = swec.erasure_coding
+    dat = np.random.default_rng(dat_size).integers(0, 256, dat_size, dtype=np.uint8)
+    base, shards = encode_files(ec, oracle, tmp_path, dat, "blk", large=large, small=small, buffer=1 << 20)
+    assert len(shards[0]) == ec.expected_shard_size(dat_size, 10, large, small)
+    for i in (2, 11):
+        os.remove(base + ec.ToExt(i))
+    assert ec.rebuild_ec_files(base) == [2, 11]
+    want = oracle.encode_dat_image(dat, buffer_size=1 << 20, large=large, small=small)
+    for i in (2, 11):
+        assert (np.fromfile(base + ec.ToExt(i), dtype=np.uint8) == want[i]).all()
