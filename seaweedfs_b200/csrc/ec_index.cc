@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -95,22 +96,30 @@ int swec_write_sorted_file_from_idx(const char* base, const char* ext) {
     if (!base || !ext) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
     std::vector<uint8_t> idx;
     if (!read_all(std::string(base) + ".idx", &idx)) return io_err(std::string("cannot read Volume Index ") + base + ".idx");
-    // readNeedleMap: last live entry per key wins; a zero offset or deleted size removes the key
-    std::map<uint64_t, std::pair<uint32_t, uint32_t>> live;
-    for (size_t off = 0; off + kEntry <= idx.size(); off += kEntry) {
-        const uint64_t key = be64(&idx[off]);
-        const uint32_t offset = be32(&idx[off + 8]);
-        const uint32_t size = be32(&idx[off + 12]);
-        if (offset != 0 && !size_deleted(int32_t(size))) live[key] = {offset, size};
-        else live.erase(key);
+    // readNeedleMap replays the .idx into a map: a live entry (non-zero offset, size not deleted) sets the key, anything
+    // else removes it — so the LAST entry of a key alone decides whether and how the key appears.  Sorting the entries
+    // by (key, position) and keeping each key's last one gives the same file without a 30-million-node tree for a
+    // full 30 GB volume of small needles.
+    struct E { uint64_t key; uint32_t pos, offset, size; };
+    const size_t n = idx.size() / kEntry;
+    if (n > 0xFFFFFFFFull) return fail(SWEC_ERR_INVALID_ARG, "index too large");
+    std::vector<E> es(n);
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* p = &idx[i * kEntry];
+        es[i] = {be64(p), uint32_t(i), be32(p + 8), be32(p + 12)};
     }
-    std::vector<uint8_t> out(live.size() * kEntry);
-    size_t o = 0;
-    for (const auto& kv : live) {  // AscendingVisit
-        put_be64(&out[o], kv.first);
-        put_be32(&out[o + 8], kv.second.first);
-        put_be32(&out[o + 12], kv.second.second);
-        o += kEntry;
+    std::sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
+    std::vector<uint8_t> out;
+    out.reserve(n * kEntry);
+    for (size_t i = 0; i < n; i++) {
+        if (i + 1 < n && es[i + 1].key == es[i].key) continue;  // not the key's last word
+        const E& e = es[i];
+        if (e.offset == 0 || size_deleted(int32_t(e.size))) continue;  // the key ends deleted
+        uint8_t rec[kEntry];
+        put_be64(rec, e.key);
+        put_be32(rec + 8, e.offset);
+        put_be32(rec + 12, e.size);
+        out.insert(out.end(), rec, rec + kEntry);  // ascending keys: AscendingVisit
     }
     if (!write_all(std::string(base) + ext, out)) return io_err("failed to open ecx file");
     return SWEC_OK;
