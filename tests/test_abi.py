@@ -227,3 +227,35 @@ def test_jit_source_compiles_for_sm100a_without_gpu(swec):
         assert rc == 0, L.swec_last_error()
         assert size.value > 1000 and steps.value <= 7 * rows.shape[0]
         print(rows.shape, size.value, steps.value, xors.value, round(time.perf_counter() - t0, 3))
+
+
+def test_layout_arithmetic_fuzz_against_oracle(swec, oracle):
+    """LocateData / ToShardIdAndOffset / expected shard size for random block sizes, ratios, volume sizes and reads:
+    libswec against the oracle's restatement of ec_locate.go:16-98 and disk_location_ec.go:428-448 (hypothesis)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    from oracle import rs_numpy as rn
+    ec = swec.erasure_coding
+
+    @settings(max_examples=300, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(k=st.integers(1, 20), small=st.integers(1, 300), mult=st.integers(1, 50), rows=st.integers(0, 4),
+           extra=st.integers(0, 20000), off_frac=st.floats(0, 1), size=st.integers(1, 5000))
+    def check(k, small, mult, rows, extra, off_frac, size):
+        large = small * mult
+        dat_size = rows * large * k + extra
+        sizes = (ec.expected_shard_size(dat_size, k, large, small), oracle.expected_shard_size(dat_size, k, large, small),
+                 rn.expected_shard_size(dat_size, k, large, small))
+        assert sizes[0] == sizes[1] == sizes[2], sizes
+        if dat_size == 0:
+            return
+        offset = int(off_frac * (dat_size - 1))
+        size = min(size, dat_size - offset)
+        shard_dat_size = dat_size // k
+        got = ec.locate_data(large, small, shard_dat_size, offset, size, k)
+        want = rn.locate_data(large, small, shard_dat_size, offset, size, k)
+        assert [tuple(g) for g in got] == [tuple(w) for w in want], (k, large, small, dat_size, offset, size)
+        assert sum(g[2] for g in got) == size
+        for iv in got:
+            assert ec.interval_to_shard(iv, large, small, k) == rn.interval_to_shard(iv, large, small, k)
+
+    check()
