@@ -24,6 +24,7 @@
  *   swec_ec_shards_rebuild      VolumeEcShardsRebuild  (file work)   weed/server/volume_grpc_erasure_coding.go:149-225
  *   swec_ec_shards_to_volume    VolumeEcShardsToVolume (file work)   weed/server/volume_grpc_erasure_coding.go:578-668
  *   swec_read_ec_needles        Store.ReadEcShardNeedle (local shards, batched)   weed/storage/store_ec.go:252-355,482-560
+ *   swec_check_index_file       idx.CheckIndexFile / EcVolume.ScrubIndex   weed/storage/idx/check.go:36-111
  *   swec_locate_data            LocateData                weed/storage/erasure_coding/ec_locate.go:16-53
  *   swec_expected_shard_size    calculateExpectedShardSize   weed/storage/disk_location_ec.go:428-448
  *
@@ -243,6 +244,11 @@ int swec_write_sorted_file_from_idx(const char *base_file_name, const char *ext)
 int swec_rebuild_ecx_file(const char *base_file_name);
 /* WriteIdxFileFromEcIndex: .ecx (+ one tombstone per .ecj id) → .idx (ec_decoder.go:35-60).       */
 int swec_write_idx_file_from_ec_index(const char *base_file_name);
+/* idx.CheckIndexFile (weed/storage/idx/check.go:36-111) = EcVolume.ScrubIndex on an .ecx (or an .idx): entries
+ * processed, and one message per finding — overlapping neighbours in (offset, size) order, a file that is not a whole
+ * number of entries — newline-separated into errors[errors_cap] (may be NULL), worded like the reference.        */
+int swec_check_index_file(const char *path, int needle_version, int64_t *entries, char *errors,
+                          size_t errors_cap, int *n_errors);
 /* HasLiveNeedles / FindDatFileSize (ec_decoder.go:23-33, 65-92).                                  */
 int swec_has_live_needles(const char *index_base_file_name, int *has_live);
 int swec_find_dat_file_size(const char *data_base_file_name, const char *index_base_file_name,

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "swec_write_sorted_file_from_idx": (C.c_int, [C.c_char_p, C.c_char_p]),
     "swec_rebuild_ecx_file": (C.c_int, [C.c_char_p]),
     "swec_write_idx_file_from_ec_index": (C.c_int, [C.c_char_p]),
+    "swec_check_index_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
     "swec_has_live_needles": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "swec_find_dat_file_size": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "swec_expected_shard_size": (C.c_int64, [C.c_int64, C.c_int, C.c_int64, C.c_int64]),

@@ -201,6 +201,56 @@ int swec_has_live_needles(const char* index_base, int* has_live) {
     return SWEC_OK;
 }
 
+// idx.CheckIndexFile (weed/storage/idx/check.go:36-111) — what EcVolume.ScrubIndex runs on .ecx
+// (ec_volume_scrub.go:20-25): entries sorted by (offset, size); two neighbours overlap when the later one starts at
+// or before the end of the earlier one; and the file must be a whole number of entries.
+int swec_check_index_file(const char* path, int needle_version, int64_t* entries, char* errors, size_t errors_cap,
+                          int* n_errors) {
+    if (!path || !entries || !n_errors) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::vector<uint8_t> raw;
+    if (!read_all(path, &raw)) return io_err(std::string("cannot read index ") + path);
+    struct E { int index; uint64_t id; int64_t offset; int32_t size; };
+    std::vector<E> es;
+    for (size_t off = 0; off + kEntry <= raw.size(); off += kEntry)  // WalkIndexFile ignores a trailing partial entry
+        es.push_back({int(es.size()), be64(&raw[off]), int64_t(be32(&raw[off + 8])) * 8, int32_t(be32(&raw[off + 12]))});
+    std::stable_sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.offset != b.offset ? a.offset < b.offset : a.size < b.size; });
+    // needle.GetActualSize with the reference's types: PaddingLength is computed in Size (int32) arithmetic and wraps
+    // like Go does; NeedleBodyLength adds in int64 (needle_read_tail.go:36-49)
+    auto actual = [&](int32_t size) -> int64_t {
+        const uint32_t tail = needle_version == 3 ? 4u + 8u : 4u;
+        const int32_t sum = int32_t(16u + uint32_t(size) + tail);  // wraps
+        const int32_t padding = 8 - (sum % 8);                      // Go's % keeps the sign of the dividend, like C++
+        return 16 + int64_t(size) + int64_t(tail) + int64_t(padding);
+    };
+    std::string text;
+    int count = 0;
+    auto add = [&](const std::string& m) {
+        if (count++) text += "\n";
+        text += m;
+    };
+    for (size_t i = 1; i < es.size(); i++) {
+        const E &e = es[i], &last = es[i - 1];
+        int64_t end = e.offset, last_end = last.offset;
+        if (const int64_t sz = actual(e.size)) end += sz - 1;
+        if (const int64_t sz = actual(last.size)) last_end += sz - 1;
+        if (e.offset <= last_end)
+            add("needle " + std::to_string(e.id) + " (#" + std::to_string(e.index + 1) + ") at [" + std::to_string(e.offset) + "-" +
+                std::to_string(end) + "] overlaps needle " + std::to_string(last.id) + " at [" + std::to_string(last.offset) + "-" +
+                std::to_string(last_end) + "]");
+    }
+    const int64_t n = int64_t(es.size());
+    if (n * kEntry != int64_t(raw.size()))
+        add("expected an index file of size " + std::to_string(raw.size()) + ", got " + std::to_string(n * kEntry));
+    *entries = n;
+    *n_errors = count;
+    if (errors && errors_cap) {
+        const size_t m = std::min(text.size(), errors_cap - 1);
+        memcpy(errors, text.data(), m);
+        errors[m] = 0;
+    }
+    return SWEC_OK;
+}
+
 int swec_find_dat_file_size(const char* data_base, const char* index_base, int64_t* dat_size) {
     if (!data_base || !index_base || !dat_size) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
     // readEcVolumeVersion: the superblock sits at the start of .ec00; byte 0 is the needle version

@@ -425,6 +425,18 @@ def write_idx_file_from_ec_index(base_file_name: str) -> None:
     check(lib().swec_write_idx_file_from_ec_index(base_file_name.encode()))
 
 
+def check_index_file(path: str, needle_version: int = 3) -> tuple[int, list[str]]:
+    """idx.CheckIndexFile (weed/storage/idx/check.go:36-111): (entries processed, findings)."""
+    n, k = C.c_int64(0), C.c_int(0)
+    buf = C.create_string_buffer(1 << 20)
+    check(lib().swec_check_index_file(path.encode(), needle_version, C.byref(n), buf, len(buf), C.byref(k)))
+    text = buf.value.decode()
+    return int(n.value), (text.split("\n") if k.value else [])
+
+
+CheckIndexFile = check_index_file
+
+
 def has_live_needles(index_base_file_name: str) -> bool:
     v = C.c_int(0)
     check(lib().swec_has_live_needles(index_base_file_name.encode(), C.byref(v)))

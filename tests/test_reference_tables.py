@@ -151,3 +151,36 @@ def test_ec_volume_file_and_delete_count_after_delete(swec, tmp_path):
     ev.DeleteNeedleFromEcx(99)                                           # not in the volume
     assert ev.FileAndDeleteCount() == (2, 1)
     ev.close()
+
+
+# ---- TestCheckIndexFile (weed/storage/idx/check_test.go:11-108): the reference's six index fixtures with the counts
+# ---- and the exact findings its test expects — K11 of oracle/README.md.  EcVolume.ScrubIndex runs this on .ecx.
+IDX_FIXTURES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "idx_test_files")
+CHECK_INDEX_CASES = [
+    ("simple_index.idx", 161, []),
+    ("deleted_files.idx", 230, []),
+    ("simple_index_bitrot.idx", 161, [
+        "needle 3544668469065756977 (#2) at [6602459528-7427766999] overlaps needle 49 at [6602459528-7427766999]",
+        "expected an index file of size 2577, got 2576"]),
+    ("simple_index_truncated.idx", 158, ["expected an index file of size 2540, got 2528"]),
+    ("deleted_files.ecx", 116, []),
+    ("deleted_files_bitrot.ecx", 116, [
+        "needle 3223857 (#110) at [6602459528-7427767055] overlaps needle 12593 at [6601933184-7407907279]",
+        "needle 3544668469065757234 (#43) at [6737203600-7579354079] overlaps needle 3223857 at [6602459528-7427767055]",
+        "needle 3421236 (#112) at [7006693800-7899362591] overlaps needle 3544668469065757234 at [6737203600-7579354079]",
+        "needle 310 (#113) at [7276179888-8185702583] overlaps needle 3421236 at [7006693800-7899362591]",
+        "needle 7089336938131513954 (#52) at [13204919056-13205053935] overlaps needle 27410143614427489 at [13070174984-14703946887]",
+        "needle 25186 (#50) at [13204919056-14855533967] overlaps needle 7089336938131513954 at [13204919056-13205053935]",
+        "needle 7089336938131513954 (#51) at [13204919056-14855533967] overlaps needle 25186 at [13204919056-14855533967]",
+        "expected an index file of size 1857, got 1856"]),
+]
+
+
+@pytest.mark.parametrize("name,want_count,want_errs", CHECK_INDEX_CASES, ids=[c[0] for c in CHECK_INDEX_CASES])
+def test_check_index_file_on_reference_fixtures(swec, name, want_count, want_errs):
+    path = os.path.join(IDX_FIXTURES, name)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/idx_test_files not shipped")
+    count, errs = swec.erasure_coding.CheckIndexFile(path, 3)
+    assert count == want_count
+    assert errs == want_errs
