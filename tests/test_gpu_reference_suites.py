@@ -202,9 +202,11 @@ def test_parity_shard_recovery(cuda, swec, oracle, parity_shard):
 # ---- disk_location_ec_realworld_test.go ------------------------------------------------------------
 
 @pytest.mark.parametrize("dat_size", [1, 1024, 10 * 1024, 1 << 20, (1 << 20) + 1, 9 * (1 << 20) + 900 * 1024,
-                                      10 * (1 << 20) + 100 * 1024])
+                                      10 * (1 << 20) + 100 * 1024,
+                                      # TestCalculateExpectedShardSizeWithRealEncoding (:13-129)
+                                      5 << 20, 10 << 20, 15 << 20, 50 << 20, 100 << 20, 512 << 20])
 def test_calculate_expected_shard_size_with_real_encoding(cuda, swec, oracle, tmp_path, dat_size):
-    """TestCalculateExpectedShardSizeEdgeCases (disk_location_ec_realworld_test.go:131-200): WriteEcFiles on
+    """TestCalculateExpectedShardSizeEdgeCases / …WithRealEncoding (disk_location_ec_realworld_test.go:13-200): WriteEcFiles on
     byte(i % 256) data, every shard file has the size calculateExpectedShardSize predicts."""
     ec = swec.erasure_coding
     dat = (np.arange(dat_size, dtype=np.int64) % 256).astype(np.uint8)

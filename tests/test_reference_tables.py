@@ -184,3 +184,10 @@ def test_check_index_file_on_reference_fixtures(swec, name, want_count, want_err
     count, errs = swec.erasure_coding.CheckIndexFile(path, 3)
     assert count == want_count
     assert errs == want_errs
+
+
+@pytest.mark.parametrize("dat_size,actual_shard,valid", [(10 * GB, GB, True), (10 * GB, GB - 1, False), (10 * GB, GB + 1, False),
+                                                         (5 * MB, MB, True), (5 * MB, 500 * 1024, False)])
+def test_shard_size_validation_scenarios(swec, dat_size, actual_shard, valid):
+    """TestShardSizeValidationScenarios (disk_location_ec_shard_size_test.go:145-200)"""
+    assert (swec.erasure_coding.expected_shard_size(dat_size) == actual_shard) is valid
