@@ -209,7 +209,7 @@ def test_calculate_expected_shard_size_with_real_encoding(cuda, swec, oracle, tm
     """TestCalculateExpectedShardSizeEdgeCases / …WithRealEncoding (disk_location_ec_realworld_test.go:13-200): WriteEcFiles on
     byte(i % 256) data, every shard file has the size calculateExpectedShardSize predicts."""
     ec = swec.erasure_coding
-    dat = (np.arange(dat_size, dtype=np.int64) % 256).astype(np.uint8)
+    dat = np.tile(np.arange(256, dtype=np.uint8), dat_size // 256 + 1)[:dat_size]        # byte(i % 256)
     base, shards = encode_files(ec, oracle, tmp_path, dat, "edge", large=1 << 30, small=1 << 20, buffer=256 * 1024)
     want = ec.expected_shard_size(dat_size)
     assert all(os.path.getsize(base + ec.ToExt(i)) == want for i in range(14))
