@@ -125,6 +125,11 @@ int swec_reconstruct_batch(swec_encoder *enc, const swec_reconstruct_item *items
 int swec_encode_multi(swec_encoder *const *encs, int n_encs, uint8_t *const *shards, size_t shard_len);
 int swec_reconstruct_multi(swec_encoder *const *encs, int n_encs, uint8_t *const *shards,
                            const uint8_t *present, size_t shard_len, int data_only);
+/* n_shards pinned buffers of shard_len bytes laid out FOR such a call: byte range g of every shard is bound to the
+ * NUMA node of encs[g]'s GPU (the split rule is shared), so each GPU DMAs from its own socket.  One allocation:
+ * release it with swec_free_pinned(shards[0]).                                                                */
+int swec_alloc_pinned_shards(swec_encoder *const *encs, int n_encs, int n_shards, size_t shard_len,
+                             uint8_t **shards);
 /* *ok = 1 iff the parity shards match the data shards.                                         */
 int swec_verify(swec_encoder *enc, uint8_t *const *shards, size_t shard_len, int *ok);
 

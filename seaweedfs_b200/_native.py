@@ -63,6 +63,7 @@ PROTOTYPES = {
     "swec_reconstruct_batch": (C.c_int, [C.c_void_p, C.POINTER(ReconstructItem), C.c_int]),
     "swec_encode_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "swec_reconstruct_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "swec_alloc_pinned_shards": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
     "swec_verify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "swec_encode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "swec_reconstruct_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

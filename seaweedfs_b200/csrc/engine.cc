@@ -803,14 +803,21 @@ int swec_reconstruct_batch(swec_encoder* e, const swec_reconstruct_item* items, 
 
 namespace {
 
-template <class Fn>  // fn(g, offset, len) → status, run concurrently for every non-empty range
-int split_columns(int n_encs, size_t n, Fn&& fn) {
-    // 4 KiB granularity keeps every range page- and 16-byte aligned relative to the caller's buffers
+// THE split rule (swec_encode_multi, swec_reconstruct_multi, swec_alloc_pinned_shards agree on it): range g of n
+// bytes over n_encs handles starts at begin[g]; 4 KiB granularity keeps every range page- and 16-byte aligned
+// relative to the caller's buffers
+std::vector<size_t> column_split(int n_encs, size_t n) {
     const size_t gran = 4096;
     const size_t units = (n + gran - 1) / gran;
     std::vector<size_t> begin(size_t(n_encs) + 1, 0);
     for (int g = 0; g <= n_encs; g++) begin[size_t(g)] = std::min(n, units * size_t(g) / size_t(n_encs) * gran);
     begin[size_t(n_encs)] = n;
+    return begin;
+}
+
+template <class Fn>  // fn(g, offset, len) → status, run concurrently for every non-empty range
+int split_columns(int n_encs, size_t n, Fn&& fn) {
+    const std::vector<size_t> begin = column_split(n_encs, n);
     std::vector<int> rc(size_t(n_encs), SWEC_OK);
     std::vector<std::string> msg(static_cast<size_t>(n_encs));
     std::vector<std::thread> threads;
@@ -857,6 +864,42 @@ int swec_encode_multi(swec_encoder* const* encs, int n_encs, uint8_t* const* sha
         for (int i = 0; i < total; i++) sub[i] = shards[i] + off;
         return swec_encode(encs[g], sub, len);
     });
+}
+
+// Host buffers laid out for a column-split call: byte range g of every shard lives on the NUMA node of the GPU that
+// will DMA it.  A plain pinned buffer sits on one socket, and the GPUs of the other socket then pull their ranges
+// across the inter-socket link (profiles/r01y_one_call_group_n8_*: 142 GB/s on 4 GPUs of one socket, 108 on all 8).
+int swec_alloc_pinned_shards(swec_encoder* const* encs, int n_encs, int n_shards, size_t shard_len, uint8_t** shards) {
+    int rc = check_group(encs, n_encs);
+    if (rc) return rc;
+    if (!shards || n_shards <= 0 || n_shards > SWEC_MAX_SHARDS || shard_len == 0) return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    const size_t pitch = (shard_len + 4095) & ~size_t(4095);
+    const size_t total = pitch * size_t(n_shards);
+    void* base = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return fail(SWEC_ERR_NOMEM, "mmap of the shard buffers failed");
+    const std::vector<size_t> begin = column_split(n_encs, shard_len);
+    if (!getenv("SWEC_NO_NUMA"))
+        for (int g = 0; g < n_encs; g++) {
+            const int node = device_numa_node(encs[g]->device);
+            if (node < 0 || node >= 1024) continue;
+            unsigned long mask[16] = {0};
+            mask[size_t(node) / (8 * sizeof(unsigned long))] |= 1ul << (size_t(node) % (8 * sizeof(unsigned long)));
+            // the end of the last range is rounded up to the page so that the tail page has a home too
+            const size_t lo = begin[size_t(g)], hi = g + 1 == n_encs ? pitch : begin[size_t(g) + 1];
+            for (int i = 0; i < n_shards && hi > lo; i++)  // MPOL_PREFERRED (1): never fails the allocation
+                syscall(SYS_mbind, static_cast<uint8_t*>(base) + size_t(i) * pitch + lo, hi - lo, 1, mask, sizeof(mask) * 8, 0);
+        }
+    const cudaError_t e = cudaHostRegister(base, total, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        munmap(base, total);
+        return cuda_fail(e, "cudaHostRegister of the shard buffers");
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pin_mapped[base] = total;
+    }
+    for (int i = 0; i < n_shards; i++) shards[i] = static_cast<uint8_t*>(base) + size_t(i) * pitch;
+    return SWEC_OK;
 }
 
 int swec_reconstruct_multi(swec_encoder* const* encs, int n_encs, uint8_t* const* shards, const uint8_t* present,

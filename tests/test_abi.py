@@ -175,6 +175,13 @@ def test_multi_handle_argument_validation(swec):
     assert L.swec_reconstruct_multi(*group(a, b), ptrs, few, 8192, 0) == -2
     allp = (C.c_uint8 * 14)(*([1] * 14))
     assert L.swec_reconstruct_multi(*group(a, b), ptrs, allp, 8192, 0) == 0   # nothing to do
+    out = (C.c_void_p * 14)()
+    assert L.swec_alloc_pinned_shards(*group(a, a), 14, 8192, out) == -1      # group checks first
+    assert L.swec_alloc_pinned_shards(*group(a, b), 0, 8192, out) == -1
+    assert L.swec_alloc_pinned_shards(*group(a, b), 14, 0, out) == -1
+    import torch
+    if not torch.cuda.is_available():                                       # pinning needs the driver: loud, no leak
+        assert L.swec_alloc_pinned_shards(*group(a, b), 14, 8192, out) in (-3, -7)
 
 
 def test_rebuild_prechecks_need_no_gpu(swec, tmp_path):

@@ -121,6 +121,32 @@ def test_one_call_split_over_several_handles(cuda, swec, oracle, n):
     grp.close()
 
 
+def test_group_shard_buffers_are_usable_by_the_split_call(cuda, swec, oracle):
+    """swec_alloc_pinned_shards: one pinned allocation whose column ranges sit near the GPU that takes them (NUMA
+    binding is best effort); the column-split encode on those buffers equals the oracle, and they are freed whole."""
+    import ctypes as C
+    torch = cuda
+    ec = swec.erasure_coding
+    L = swec.lib()
+    ngpu = torch.cuda.device_count()
+    grp = ec.EncoderGroup(10, 4, list(range(ngpu)) if ngpu >= 2 else [0, 0])
+    n = 5_000_000 + 77
+    ptrs = (C.c_void_p * 14)()
+    assert L.swec_alloc_pinned_shards(grp._arr, len(grp.encoders), 14, n, ptrs) == 0
+    shards = [np.ctypeslib.as_array(C.cast(ptrs[i], C.POINTER(C.c_uint8)), shape=(n,)) for i in range(14)]
+    assert all(ptrs[i] % 4096 == 0 for i in range(14))
+    rng = np.random.default_rng(12)
+    for s in shards[:10]:
+        s[:] = rng.integers(0, 256, n, dtype=np.uint8)
+    want = oracle.encode(10, 4, [s.copy() for s in shards[:10]])
+    assert L.swec_encode_multi(grp._arr, len(grp.encoders), ptrs, n) == 0
+    for p in range(4):
+        assert (shards[10 + p] == want[p]).all()
+    del shards
+    L.swec_free_pinned(ptrs[0])
+    grp.close()
+
+
 def test_concurrent_file_level_calls_share_parked_rings(cuda, swec, oracle, tmp_path):
     """Several volumes encoded and rebuilt at once from different OS threads (the shell's ec.encode runs up to ten,
     weed/shell/common.go:11), twice over, so that later calls pick up staging rings parked by earlier ones while
