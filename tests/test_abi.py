@@ -266,3 +266,50 @@ def test_layout_arithmetic_fuzz_against_oracle(swec, oracle):
             assert ec.interval_to_shard(iv, large, small, k) == rn.interval_to_shard(iv, large, small, k)
 
     check()
+
+
+def _split_top_level(args: str) -> list[str]:
+    out, depth, cur = [], 0, ""
+    for ch in args:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    return [a for a in out + [cur] if a.strip()]
+
+
+def test_cgo_shim_calls_match_the_header():
+    """Go is not installed here, so the shim (integration/go/ec_swec.go, also quoted in INTEGRATION.md) cannot be
+    compiled; at least every C.swec_* call in it must name a function include/swec.h declares, with the declared
+    number of arguments, and every C.SWEC_* constant must exist."""
+    header = open(os.path.join(ROOT, "include", "swec.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(swec_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        params = m.group(2).strip()
+        decls[m.group(1)] = 0 if params in ("", "void") else len(_split_top_level(params))
+    go = open(os.path.join(ROOT, "integration", "go", "ec_swec.go")).read()
+    calls = 0
+    for m in re.finditer(r"C\.(swec_\w+)\(", go):
+        name = m.group(1)
+        if name in ("swec_encoder", "swec_ec_volume", "swec_needle_read"):      # type names used in conversions
+            continue
+        assert name in decls, f"{name} is not declared in swec.h"
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(go[i], 0)
+            i += 1
+        args = _split_top_level(go[m.end():i - 1])
+        assert len(args) == decls[name], f"{name}: shim passes {len(args)} arguments, header declares {decls[name]}"
+        calls += 1
+    assert calls >= 15
+    for const in set(re.findall(r"C\.(SWEC_\w+)", go)):
+        assert re.search(rf"\b{const}\b", header), const
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```go\n(//go:build swec && cgo.*?)```", md, re.S).group(1)
+    assert block.strip() in go, "INTEGRATION.md's listing and integration/go/ec_swec.go have drifted apart"
