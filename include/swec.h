@@ -236,6 +236,13 @@ int swec_ec_volume_read_needles(swec_ec_volume *vol, swec_needle_read *reads, in
 /* EcVolume.DeleteNeedleFromEcx (ec_volume_delete.go:28-93): append the id to the .ecj journal (fsync'ed
  * before it becomes visible to reads); unknown, tombstoned or already journalled ids are not errors.  */
 int swec_ec_volume_delete_needle(swec_ec_volume *vol, uint64_t needle_id);
+/* EcVolume.ScrubLocal (ec_volume_scrub.go:27-118) without the needle parse: ScrubIndex (swec_check_index_file on the
+ * .ecx), then every live entry is located and each of its chunks read from the local shard that should hold it.
+ * broken_shards[SWEC_MAX_SHARDS] receives the ids (ascending) of shards that were too short or unreadable for some
+ * chunk; findings are newline-separated in errors[], worded like the reference.  Parity is checked by
+ * swec_verify_ec_files, record CRCs by the storage engine.                                                    */
+int swec_ec_volume_scrub_local(swec_ec_volume *vol, int64_t *entries, uint32_t *broken_shards, int *n_broken,
+                               char *errors, size_t errors_cap, int *n_errors);
 /* EcVolume.FileAndDeleteCount (ec_volume.go:330-349): .ecx entries, distinct journalled deletions.      */
 int swec_ec_volume_counts(swec_ec_volume *vol, uint64_t *file_count, uint64_t *delete_count);
 void swec_ec_volume_close(swec_ec_volume *vol);

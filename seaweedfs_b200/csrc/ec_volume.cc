@@ -496,6 +496,100 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
     return SWEC_OK;
 }
 
+// EcVolume.ScrubLocal (ec_volume_scrub.go:27-118) minus the needle parse: ScrubIndex, then every live entry of .ecx is
+// located (GetActualSize ONCE here, unlike the read path) and each of its chunks read from the local shard that holds it.
+// A shard that is too short for a chunk, or cannot be read, is reported broken; chunks on shards that are not local are
+// skipped like the reference skips remote ones.  The CRC of the record belongs to the storage engine's needle parser.
+int swec_ec_volume_scrub_local(swec_ec_volume* v, int64_t* entries, uint32_t* broken_shards, int* n_broken, char* errors,
+                               size_t errors_cap, int* n_errors) {
+    if (!v || !entries || !n_broken || !n_errors || !broken_shards) return fail(SWEC_ERR_INVALID_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    std::string text;
+    int count = 0;
+    auto add = [&](const std::string& m) {
+        if (count++) text += "\n";
+        text += m;
+    };
+    {  // ScrubIndex = idx.CheckIndexFile on the sealed index
+        int64_t n = 0;
+        int k2 = 0;
+        std::vector<char> buf(size_t(1) << 20);
+        const int rc = swec_check_index_file((v->index_base + ".ecx").c_str(), v->version, &n, buf.data(), buf.size(), &k2);
+        if (rc) return rc;
+        if (k2) add(buf.data()), count += k2 - 1;
+    }
+    const int k = v->k, total = v->k + v->m;
+    const int64_t large = int64_t(1) << 30, small = int64_t(1) << 20;
+    std::vector<int64_t> shard_size(size_t(total), -1);
+    for (int i = 0; i < total; i++) {
+        struct stat st;
+        if (v->shard_fd[size_t(i)] >= 0 && fstat(v->shard_fd[size_t(i)], &st) == 0) shard_size[size_t(i)] = st.st_size;
+    }
+    std::vector<uint8_t> broken(size_t(total), 0), chunk;
+    const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
+    const int64_t n_entries = int64_t(v->ecx.size()) / 16;
+    int64_t walked = 0;
+    for (int64_t e = 0; e < n_entries; e++) {
+        walked++;
+        const uint64_t id = be64(ex + e * 16);
+        const int64_t offset = int64_t(be32(ex + e * 16 + 8)) * 8;
+        const int32_t size = int32_t(be32(ex + e * 16 + 12));
+        if (size == -1) continue;  // Size.IsTombstone
+        const int64_t want = needle_actual_size(size, v->version);
+        std::vector<swec_interval> ivs(size_t(std::max<int64_t>(want, 0) / small) + 4);
+        const int niv = want > 0 ? swec_locate_data(large, small, v->shard_dat_size, offset, want, k, ivs.data(), int(ivs.size())) : 0;
+        if (niv < 0) return niv;
+        int64_t read = 0;
+        for (int j = 0; j < niv; j++) {
+            int sid = 0;
+            int64_t soff = 0;
+            swec_interval_to_shard(&ivs[size_t(j)], large, small, k, &sid, &soff);
+            const int64_t ssize = ivs[size_t(j)].size;
+            const std::string where = std::to_string(j + 1) + "/" + std::to_string(niv);
+            if (v->shard_fd[size_t(sid)] < 0) {  // not local: skipped, counted as read
+                read += ssize;
+                continue;
+            }
+            if (soff + ssize > shard_size[size_t(sid)]) {
+                broken[size_t(sid)] = 1;
+                add("local shard " + std::to_string(sid) + " for needle " + std::to_string(id) + " is too short (" +
+                    std::to_string(shard_size[size_t(sid)]) + "), cannot read chunk " + where);
+                continue;
+            }
+            chunk.resize(size_t(ssize));
+            const ssize_t got = pread(v->shard_fd[size_t(sid)], chunk.data(), size_t(ssize), off_t(soff));
+            if (got < 0) {
+                broken[size_t(sid)] = 1;
+                add("failed to read chunk " + where + " for needle " + std::to_string(id) + " from local shard " + std::to_string(sid) +
+                    " at offset " + std::to_string(soff) + ": " + strerror(errno));
+                continue;
+            }
+            if (got != ssize) {
+                broken[size_t(sid)] = 1;
+                add("expected " + std::to_string(ssize) + " bytes for chunk " + where + " for needle " + std::to_string(id) +
+                    " from local shard " + std::to_string(sid) + ", got " + std::to_string(got));
+                continue;
+            }
+            read += got;
+        }
+        if (read != want) {  // the reference's walk stops here
+            add("expected " + std::to_string(want) + " bytes for needle " + std::to_string(id) + ", got " + std::to_string(read));
+            break;
+        }
+    }
+    *entries = walked;
+    *n_broken = 0;
+    for (int i = 0; i < total; i++)
+        if (broken[size_t(i)]) broken_shards[(*n_broken)++] = uint32_t(i);
+    *n_errors = count;
+    if (errors && errors_cap) {
+        const size_t m = std::min(text.size(), errors_cap - 1);
+        memcpy(errors, text.data(), m);
+        errors[m] = 0;
+    }
+    return SWEC_OK;
+}
+
 // FileAndDeleteCount (ec_volume.go:330-349): entries of the sealed .ecx, and distinct journalled ids.
 int swec_ec_volume_counts(swec_ec_volume* v, uint64_t* file_count, uint64_t* delete_count) {
     if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");

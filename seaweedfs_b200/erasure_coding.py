@@ -384,6 +384,16 @@ class EcVolume:
 
     FileAndDeleteCount = file_and_delete_count
 
+    def scrub_local(self):
+        """ScrubLocal (ec_volume_scrub.go:27-118): (entries walked, broken shard ids, findings)."""
+        n, nb, ne = C.c_int64(0), C.c_int(0), C.c_int(0)
+        broken = (C.c_uint32 * MaxShardCount)()
+        buf = C.create_string_buffer(1 << 20)
+        check(lib().swec_ec_volume_scrub_local(self._h, C.byref(n), broken, C.byref(nb), buf, len(buf), C.byref(ne)))
+        return int(n.value), list(broken[: nb.value]), (buf.value.decode().split("\n") if ne.value else [])
+
+    ScrubLocal = scrub_local
+
     def close(self) -> None:
         h, self._h = getattr(self, "_h", None), None
         if h and callable(lib):

@@ -422,3 +422,22 @@ def test_read_ec_needle_spanning_many_blocks(swec, oracle, tmp_path):
     r = ec.ReadEcShardNeedles(base, [77], device=-1)[0]
     want = expected_record(dat, 8, size)
     assert r["status"] == "SWEC_OK" and r["n_bytes"] == len(want) and (r["bytes"] == want).all()
+
+
+def test_scrub_local_finds_short_shards(swec, oracle, tmp_path):
+    """ScrubLocal (ec_volume_scrub.go:27-118): a healthy volume walks clean; a truncated shard file is reported broken
+    with the reference's wording; a shard that is not local is skipped."""
+    ec = swec.erasure_coding
+    base, dat, live = needle_volume(oracle, tmp_path, seed=61)
+    n_entries = len(live)
+    vol = ec.EcVolume(base, device=-1)
+    assert vol.ScrubLocal() == (n_entries, [], [])
+    vol.close()
+    os.remove(base + ".ec09")                                             # not local: its chunks are skipped
+    size0 = os.path.getsize(base + ".ec00")                               # two small rows: 2 MiB
+    os.truncate(base + ".ec00", size0 // 2)                               # the second row's block of shard 0 is gone
+    vol = ec.EcVolume(base, device=-1)
+    count, broken, findings = vol.ScrubLocal()
+    assert count == n_entries and broken == [0]
+    assert findings and all(f.startswith("local shard 0 for needle ") and f"is too short ({size0 // 2})" in f for f in findings)
+    vol.close()
