@@ -25,6 +25,8 @@
  *   swec_ec_shards_to_volume    VolumeEcShardsToVolume (file work)   weed/server/volume_grpc_erasure_coding.go:578-668
  *   swec_read_ec_needles        Store.ReadEcShardNeedle (local shards, batched)   weed/storage/store_ec.go:252-355,482-560
  *   swec_check_index_file       idx.CheckIndexFile / EcVolume.ScrubIndex   weed/storage/idx/check.go:36-111
+ *   swec_ec_volume_*            EcVolume: mount, ReadEcShardNeedle, DeleteNeedleFromEcx, FileAndDeleteCount, ScrubLocal
+ *                                                          weed/storage/erasure_coding/ec_volume.go, ec_volume_delete.go, ec_volume_scrub.go
  *   swec_locate_data            LocateData                weed/storage/erasure_coding/ec_locate.go:16-53
  *   swec_expected_shard_size    calculateExpectedShardSize   weed/storage/disk_location_ec.go:428-448
  *
