@@ -301,3 +301,48 @@ def find_dat_file_size(ecx: bytes, version: int) -> int:
         fixed = 16 + size + 4 + (8 if version == 3 else 0)
         best = max(best, offset * 8 + fixed + (8 - fixed % 8))
     return best
+
+
+def _i32(v: int) -> int:
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def get_actual_size(size: int, version: int) -> int:
+    """needle.GetActualSize with the reference's types (needle_read.go:292-294, needle_read_tail.go:36-49):
+    PaddingLength is evaluated in Size (int32) arithmetic — it wraps, and Go's % keeps the dividend's sign —
+    while NeedleBodyLength adds in int64."""
+    tail = 12 if version == 3 else 4
+    s = _i32(16 + size + tail)
+    rem = abs(s) % 8
+    rem = -rem if s < 0 else rem
+    return 16 + size + tail + (8 - rem)
+
+
+def check_index_file(raw: bytes, version: int = 3):
+    """idx.CheckIndexFile (weed/storage/idx/check.go:36-111): entries in (offset, size) order; a finding for every
+    neighbour that starts at or before the end of its predecessor; a finding when the file is not a whole number of
+    entries.  Returns (entries processed, findings)."""
+    es = [(i, k, o * 8, s) for i, (k, o, s) in enumerate(_entries(raw))]
+    es.sort(key=lambda e: (e[2], e[3]))                      # stable, like the run of equal keys in the fixtures
+    errs = []
+    for j in range(1, len(es)):
+        idx, key, off, size = es[j]
+        _, lkey, loff, lsize = es[j - 1]
+        end = off + (get_actual_size(size, version) - 1 if get_actual_size(size, version) else 0)
+        lend = loff + (get_actual_size(lsize, version) - 1 if get_actual_size(lsize, version) else 0)
+        if off <= lend:
+            errs.append(f"needle {key} (#{idx + 1}) at [{off}-{end}] overlaps needle {lkey} at [{loff}-{lend}]")
+    if len(es) * 16 != len(raw):
+        errs.append(f"expected an index file of size {len(raw)}, got {len(es) * 16}")
+    return len(es), errs
+
+
+def read_needle_record(dat: np.ndarray, offset: int, size: int, version: int = 3) -> np.ndarray:
+    """The bytes Store.ReadEcShardNeedle hands to the needle parser (store_ec.go:252-290): LocateEcShardNeedle
+    passes GetActualSize(size) to LocateEcShardNeedleInterval, which applies GetActualSize again
+    (ec_volume.go:395,414), so the read runs past the record; past the end of the volume the shards hold the
+    zero padding of the last small row."""
+    want = get_actual_size(get_actual_size(size, version), version)
+    padded = np.concatenate([dat, np.zeros(want + 16, dtype=np.uint8)])
+    return padded[offset:offset + want]

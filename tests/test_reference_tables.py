@@ -184,6 +184,25 @@ def test_check_index_file_on_reference_fixtures(swec, name, want_count, want_err
     count, errs = swec.erasure_coding.CheckIndexFile(path, 3)
     assert count == want_count
     assert errs == want_errs
+    assert rn.check_index_file(open(path, "rb").read(), 3) == (want_count, want_errs)      # the oracle's restatement too
+
+
+def test_check_index_file_fuzz_against_oracle(swec, tmp_path):
+    """Random indexes with overlaps, tombstones, zero and huge sizes and ragged tails: product == oracle."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for case in range(60):
+        n = int(rng.integers(0, 60))
+        raw = b""
+        for _ in range(n):
+            size = int(rng.choice([rng.integers(0, 5000), -1, -int(rng.integers(2, 5000)), 0x7FFFFFF0 + int(rng.integers(0, 15)),
+                                   int(rng.integers(0, 1 << 31))]))
+            raw += rn._entry(int(rng.integers(1, 1 << 40)), int(rng.integers(0, 3000)), size)
+        raw += bytes(int(rng.integers(0, 16)) if case % 3 == 0 else 0)
+        path = tmp_path / f"f{case}.ecx"
+        path.write_bytes(raw)
+        for version in (2, 3):
+            assert swec.erasure_coding.CheckIndexFile(str(path), version) == rn.check_index_file(raw, version), (case, version)
 
 
 @pytest.mark.parametrize("dat_size,actual_shard,valid", [(10 * GB, GB, True), (10 * GB, GB - 1, False), (10 * GB, GB + 1, False),

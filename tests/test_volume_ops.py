@@ -153,14 +153,8 @@ def test_ec_shards_rebuild_prechecks_need_no_gpu(swec, oracle, tmp_path):
 
 
 def expected_record(dat, offset, size, version=3):
-    """What ReadEcShardNeedle's `bytes` holds: GetActualSize applied twice (ec_volume.go:395,414), taken from
-    the volume image zero-padded the way the last small row is."""
-    def actual(sz):
-        fixed = 16 + sz + 4 + (8 if version == 3 else 0)
-        return fixed + (8 - fixed % 8)
-    want = actual(actual(size))
-    padded = np.concatenate([dat, np.zeros(want + 16, dtype=np.uint8)])
-    return padded[offset:offset + want]
+    """What ReadEcShardNeedle's `bytes` holds — the oracle's restatement (GetActualSize applied twice)."""
+    return rn.read_needle_record(dat, offset, size, version)
 
 
 def needle_volume(oracle, tmp_path, seed=17, with_vif=True):
