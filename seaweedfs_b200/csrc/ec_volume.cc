@@ -14,6 +14,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <libgen.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -257,7 +258,11 @@ struct swec_ec_volume {
     int64_t shard_dat_size = 0;
     std::string index_base;
     std::vector<int> shard_fd;  // total entries, -1 = not local
-    std::string ecx, ecj;
+    // the sealed index is mapped, not copied: a full volume of small needles has a ~500 MB .ecx and a server mounts
+    // hundreds of EC volumes; a lookup touches ~25 pages of the page cache (the reference does 25 ReadAt calls)
+    const uint8_t* ecx_map = nullptr;
+    size_t ecx_bytes = 0;
+    std::string ecj;
     std::vector<uint64_t> deleted;  // ids of .ecj, sorted and unique: the reference's in-memory deletedNeedles set
     int64_t ecj_size_seen = -1;
     void index_journal() {
@@ -273,6 +278,7 @@ struct swec_ec_volume {
     void refresh_journal(bool force = false);
     swec_encoder* enc = nullptr;  // created on the first recovery, keeps its staging ring and kernels
     ~swec_ec_volume() {
+        if (ecx_map && ecx_bytes) munmap(const_cast<uint8_t*>(ecx_map), ecx_bytes);
         for (int fd : shard_fd)
             if (fd >= 0) close(fd);
         if (enc) swec_encoder_free(enc);
@@ -349,7 +355,28 @@ int swec_ec_volume_open(const char* data_base, const char* index_base, const cha
     // LocateEcShardNeedleInterval: .vif's datFileSize is authoritative; old volumes fall back to the
     // shard file size minus one (ec_volume.go:399-417)
     v->shard_dat_size = dat_file_size > 0 ? dat_file_size / v->k : ecd_file_size - 1;
-    if (!slurp(ib + ".ecx", &v->ecx)) return fail(SWEC_ERR_IO, "cannot open ec volume index " + ib + ".ecx: " + strerror(errno));
+    {
+        const int efd = open((ib + ".ecx").c_str(), O_RDONLY);
+        if (efd < 0) return fail(SWEC_ERR_IO, "cannot open ec volume index " + ib + ".ecx: " + strerror(errno));
+        struct stat st;
+        if (fstat(efd, &st) != 0) {
+            const int e = errno;
+            close(efd);
+            return fail(SWEC_ERR_IO, "can not stat ec volume index " + ib + ".ecx: " + strerror(e));
+        }
+        v->ecx_bytes = size_t(st.st_size);
+        if (v->ecx_bytes) {  // MAP_SHARED: tombstones that RebuildEcxFile writes in place are seen
+            void* m = mmap(nullptr, v->ecx_bytes, PROT_READ, MAP_SHARED, efd, 0);
+            if (m == MAP_FAILED) {
+                const int e = errno;
+                close(efd);
+                v->ecx_bytes = 0;
+                return fail(SWEC_ERR_IO, "cannot map ec volume index " + ib + ".ecx: " + strerror(e));
+            }
+            v->ecx_map = static_cast<const uint8_t*>(m);
+        }
+        close(efd);
+    }
     *out = v.release();
     return SWEC_OK;
 }
@@ -363,8 +390,8 @@ int swec_ec_volume_read_needles(swec_ec_volume* v, swec_needle_read* reads, int 
     const int64_t large = int64_t(1) << 30, small = int64_t(1) << 20;
 
     v->refresh_journal();
-    const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
-    const int64_t entries = int64_t(v->ecx.size()) / 16;
+    const uint8_t* ex = v->ecx_map;
+    const int64_t entries = int64_t(v->ecx_bytes) / 16;
     auto journalled = [&](uint64_t id) { return std::binary_search(v->deleted.begin(), v->deleted.end(), id); };
 
     // ---- pass 1: locate every needle, read what is local, collect what must be recovered
@@ -526,8 +553,8 @@ int swec_ec_volume_scrub_local(swec_ec_volume* v, int64_t* entries, uint32_t* br
         if (v->shard_fd[size_t(i)] >= 0 && fstat(v->shard_fd[size_t(i)], &st) == 0) shard_size[size_t(i)] = st.st_size;
     }
     std::vector<uint8_t> broken(size_t(total), 0), chunk;
-    const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
-    const int64_t n_entries = int64_t(v->ecx.size()) / 16;
+    const uint8_t* ex = v->ecx_map;
+    const int64_t n_entries = int64_t(v->ecx_bytes) / 16;
     int64_t walked = 0;
     for (int64_t e = 0; e < n_entries; e++) {
         walked++;
@@ -595,7 +622,7 @@ int swec_ec_volume_counts(swec_ec_volume* v, uint64_t* file_count, uint64_t* del
     if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");
     std::lock_guard<std::mutex> lock(v->mu);
     v->refresh_journal();
-    if (file_count) *file_count = uint64_t(v->ecx.size() / 16);
+    if (file_count) *file_count = uint64_t(v->ecx_bytes / 16);
     if (delete_count) *delete_count = uint64_t(v->deleted.size());
     return SWEC_OK;
 }
@@ -606,8 +633,8 @@ int swec_ec_volume_counts(swec_ec_volume* v, uint64_t* file_count, uint64_t* del
 int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
     if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");
     std::lock_guard<std::mutex> lock(v->mu);
-    const uint8_t* ex = reinterpret_cast<const uint8_t*>(v->ecx.data());
-    int64_t lo = 0, hi = int64_t(v->ecx.size()) / 16, found = -1;
+    const uint8_t* ex = v->ecx_map;
+    int64_t lo = 0, hi = int64_t(v->ecx_bytes) / 16, found = -1;
     while (lo < hi) {
         const int64_t mid = (lo + hi) / 2;
         const uint64_t key = be64(ex + mid * 16);
