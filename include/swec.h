@@ -245,6 +245,11 @@ int swec_ec_volume_delete_needle(swec_ec_volume *vol, uint64_t needle_id);
  * swec_verify_ec_files, record CRCs by the storage engine.                                                    */
 int swec_ec_volume_scrub_local(swec_ec_volume *vol, int64_t *entries, uint32_t *broken_shards, int *n_broken,
                                char *errors, size_t errors_cap, int *n_errors);
+/* What mounting derived (NewEcVolume, ec_volume.go:114-154,399-417): EC ratio and needle version from .vif (defaults
+ * 10+4, version 3), the shard size LocateData works with, and a bit per shard file found locally.  Any out pointer
+ * may be NULL.                                                                                                 */
+int swec_ec_volume_info(swec_ec_volume *vol, int *data_shards, int *parity_shards, int *needle_version,
+                        int64_t *shard_dat_size, uint32_t *local_shard_bits);
 /* EcVolume.FileAndDeleteCount (ec_volume.go:330-349): .ecx entries, distinct journalled deletions.      */
 int swec_ec_volume_counts(swec_ec_volume *vol, uint64_t *file_count, uint64_t *delete_count);
 void swec_ec_volume_close(swec_ec_volume *vol);

@@ -90,6 +90,8 @@ PROTOTYPES = {
     "swec_ec_volume_delete_needle": (C.c_int, [C.c_void_p, C.c_uint64]),
     "swec_ec_volume_scrub_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_int),
                                              C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "swec_ec_volume_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]),
     "swec_ec_volume_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "swec_ec_volume_close": (None, [C.c_void_p]),
     "swec_write_sorted_file_from_idx": (C.c_int, [C.c_char_p, C.c_char_p]),

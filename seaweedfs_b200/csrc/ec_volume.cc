@@ -617,6 +617,24 @@ int swec_ec_volume_scrub_local(swec_ec_volume* v, int64_t* entries, uint32_t* br
     return SWEC_OK;
 }
 
+// what NewEcVolume derived from .vif and the shard files (ec_volume.go:114-154,399-417)
+int swec_ec_volume_info(swec_ec_volume* v, int* data_shards, int* parity_shards, int* needle_version, int64_t* shard_dat_size,
+                        uint32_t* local_shard_bits) {
+    if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");
+    std::lock_guard<std::mutex> lock(v->mu);
+    if (data_shards) *data_shards = v->k;
+    if (parity_shards) *parity_shards = v->m;
+    if (needle_version) *needle_version = v->version;
+    if (shard_dat_size) *shard_dat_size = v->shard_dat_size;
+    if (local_shard_bits) {
+        uint32_t bits = 0;
+        for (size_t i = 0; i < v->shard_fd.size(); i++)
+            if (v->shard_fd[i] >= 0) bits |= 1u << i;
+        *local_shard_bits = bits;
+    }
+    return SWEC_OK;
+}
+
 // FileAndDeleteCount (ec_volume.go:330-349): entries of the sealed .ecx, and distinct journalled ids.
 int swec_ec_volume_counts(swec_ec_volume* v, uint64_t* file_count, uint64_t* delete_count) {
     if (!v) return fail(SWEC_ERR_INVALID_ARG, "NULL volume");

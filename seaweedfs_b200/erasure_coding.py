@@ -376,6 +376,12 @@ class EcVolume:
 
     DeleteNeedleFromEcx = delete_needle
 
+    def info(self) -> dict:
+        k, m, ver, bits, sds = C.c_int(0), C.c_int(0), C.c_int(0), C.c_uint32(0), C.c_int64(0)
+        check(lib().swec_ec_volume_info(self._h, C.byref(k), C.byref(m), C.byref(ver), C.byref(sds), C.byref(bits)))
+        return {"data_shards": k.value, "parity_shards": m.value, "version": ver.value, "shard_dat_size": sds.value,
+                "local_shards": [i for i in range(32) if bits.value >> i & 1]}
+
     def file_and_delete_count(self) -> tuple[int, int]:
         """FileAndDeleteCount (ec_volume.go:330-349)"""
         f, d = C.c_uint64(0), C.c_uint64(0)

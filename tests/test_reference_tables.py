@@ -210,3 +210,63 @@ def test_check_index_file_fuzz_against_oracle(swec, tmp_path):
 def test_shard_size_validation_scenarios(swec, dat_size, actual_shard, valid):
     """TestShardSizeValidationScenarios (disk_location_ec_shard_size_test.go:145-200)"""
     assert (swec.erasure_coding.expected_shard_size(dat_size) == actual_shard) is valid
+
+
+# ---- the Rust twin's locate tests (seaweed-volume/src/storage/erasure_coding/ec_locate.rs:139-233) -------------
+
+def test_rust_twin_interval_to_shard_id(swec):
+    ec = swec.erasure_coding
+    L, S = 1 << 30, 1 << 20
+    # (BlockIndex, InnerBlockOffset, Size, IsLargeBlock, LargeBlockRowsCount) → (shard, offset)
+    assert ec.interval_to_shard((0, 100, 50, True, 1), L, S) == (0, 100)
+    assert ec.interval_to_shard((5, 0, 1024, True, 1), L, S)[0] == 5
+    assert ec.interval_to_shard((12, 200, 50, True, 5), L, S) == (2, L + 200)      # row 1 of shard 2
+    assert ec.interval_to_shard((10, 0, 100, True, 2), L, S) == (0, L)
+    assert ec.interval_to_shard((0, 0, 100, False, 2), L, S) == (0, 2 * L)         # test_small_block_after_large
+
+
+def test_rust_twin_locate_data_small_and_empty(swec):
+    ec = swec.erasure_coding
+    ivs = ec.LocateData(1 << 30, 1 << 20, 1 << 20, 50, 100)                        # test_locate_data_small_file
+    assert len(ivs) == 1 and ivs[0][3] is False
+    assert ec.LocateData(1 << 30, 1 << 20, 1 << 20, 0, 0) == []                    # test_locate_data_empty
+
+
+# ---- the Rust twin's EcVolume tests (seaweed-volume/src/storage/erasure_coding/ec_volume.rs:1097-1230) ----------
+
+def test_rust_twin_ec_volume_find_needle_and_journal(swec, tmp_path):
+    ec = swec.erasure_coding
+    ev = _mount_fixture(ec, tmp_path, entry(1, 8, 100) + entry(5, 200, 200) + entry(10, 504, 300), [])
+    out = ev.ReadEcShardNeedles([5, 7], capacity=16)
+    assert (out[0]["offset"], out[0]["size"]) == (200, 200)                    # found (the 16-byte buffer is too small to read into)
+    assert out[1]["status"] == "SWEC_ERR_NOT_FOUND"
+    assert ev.FileAndDeleteCount() == (3, 0)
+    ev.DeleteNeedleFromEcx(1)
+    ev.DeleteNeedleFromEcx(10)
+    assert open(str(tmp_path / "test_1.ecj"), "rb").read() == (1).to_bytes(8, "big") + (10).to_bytes(8, "big")
+    assert ev.FileAndDeleteCount() == (3, 2)
+    ev.DeleteNeedleFromEcx(1)                                                  # idempotent
+    ev.DeleteNeedleFromEcx(999)                                                # missing
+    assert ev.FileAndDeleteCount() == (3, 2)
+    ev.close()
+
+
+@pytest.mark.parametrize("vif,want", [({"dataShards": 6, "parityShards": 3}, (6, 3)),        # config from .vif
+                                      ({"dataShards": 30, "parityShards": 9}, (10, 4)),      # invalid: > MaxShardCount ⇒ defaults
+                                      ({"dataShards": 0, "parityShards": 4}, (10, 4)),
+                                      (None, (10, 4))])
+def test_ec_volume_ratio_from_vif(swec, tmp_path, vif, want):
+    """NewEcVolume (ec_volume.go:114-154): EC ratio from .vif when valid (ds > 0, ps > 0, ds + ps <= 32), else 10+4."""
+    import json
+    ec = swec.erasure_coding
+    base = str(tmp_path / "pics_1")
+    open(base + ".ecx", "wb").write(b"")
+    open(base + ".ec00", "wb").write(bytes(8))
+    if vif is not None:
+        json.dump({"version": 2, "datFileSize": "123456", "ecShardConfig": vif}, open(base + ".vif", "w"))
+    ev = ec.EcVolume(base, device=-1)
+    info = ev.info()
+    assert (info["data_shards"], info["parity_shards"]) == want
+    assert info["version"] == (2 if vif is not None else 3) and info["local_shards"] == [0]
+    assert info["shard_dat_size"] == (123456 // want[0] if vif is not None else 8 - 1)
+    ev.close()
