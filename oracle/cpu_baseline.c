@@ -413,3 +413,136 @@ int orc_generate_ec_files_simd(const char *base, int kind, int64_t bufsz, int64_
     close(fd);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-volume expected digests (CHECKER for the full-size GPU runs; test/bench infrastructure).
+ *
+ * The synthetic volume of the GPU bench is byte b = splitmix64 stream of (seed, b) (orc_synth_fill).
+ * This walks the shard space of encodeDatFile (ec_encoder.go:280-321: rows of k large blocks while
+ * remaining >= k*large, then rows of k small blocks, bytes past EOF read as zero, :258-262) in
+ * chunks, regenerates the k data columns of each chunk straight from the generator, encodes them
+ * with the reference's arithmetic (kind 0 = reference C kernel from oracle/_ref, 1 = GFNI port,
+ * 2 = the scalar restatement orc_encode's tables) and folds every shard into the same 64-bit
+ * order-sensitive digest the device computes (Σ_j splitmix64_at(word_j, j) mod 2^64 over the
+ * shard's little-endian 8-byte words).  Nothing of the volume is ever held in memory, so a 30 GiB
+ * volume costs a few seconds on a dozen cores and can be checked in full after every GPU run.
+ *   digests[0..k)   data shards (.ec00 … ), digests[k..k+m) parity shards.
+ * Returns 0, -1 (kind unavailable) or -2 (bad arguments). */
+static inline uint64_t vd_mix(uint64_t seed, uint64_t j)
+{
+    uint64_t z = seed + (j + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+typedef struct {
+    int kind, k, m, id, threads;
+    int64_t dat_size, large, small, shard_size, chunk;
+    uint64_t seed;
+    const uint8_t *rows;
+    const uint64_t *mats;
+    uint64_t sums[ORC_MAX_SHARDS];
+    int rc;
+} vd_job_t;
+
+static void *vd_worker(void *arg)
+{
+    vd_job_t *j = (vd_job_t *)arg;
+    const int k = j->k, m = j->m;
+    const int64_t c = j->chunk;
+    uint8_t *buf[ORC_MAX_SHARDS];
+    memset(j->sums, 0, sizeof j->sums);
+    for (int i = 0; i < k + m; i++)
+        if (posix_memalign((void **)&buf[i], 4096, (size_t)c)) { j->rc = -2; return NULL; }
+    const int64_t large_row = j->large * k, small_row = j->small * k;
+    const int64_t nlarge = j->dat_size / large_row;
+    const int64_t nchunks = j->shard_size / c;
+    for (int64_t ci = j->id; ci < nchunks; ci += j->threads) {
+        const int64_t off = ci * c; /* offset inside every shard file */
+        for (int i = 0; i < k; i++) {
+            int64_t src; /* .dat offset of shard i's bytes [off, off+c) */
+            if (off < nlarge * j->large) src = (off / j->large) * large_row + i * j->large + off % j->large;
+            else {
+                const int64_t o2 = off - nlarge * j->large;
+                src = nlarge * large_row + (o2 / j->small) * small_row + i * j->small + o2 % j->small;
+            }
+            uint64_t *w = (uint64_t *)buf[i];
+            const int64_t have = j->dat_size - src; /* bytes of this run that exist in the .dat */
+            const int64_t nw = c / 8;
+            for (int64_t x = 0; x < nw; x++) {
+                const int64_t b = 8 * x;
+                uint64_t v = 0;
+                if (b < have) {
+                    v = vd_mix(j->seed, (uint64_t)(src + b) >> 3);
+                    if (b + 8 > have) v &= (~0ull) >> (8 * (8 - (have - b))); /* ragged EOF inside a word */
+                }
+                w[x] = v;
+            }
+        }
+        if (j->kind == 2) {
+            const uint8_t *mt = orc_mul_table();
+            for (int p = 0; p < m; p++) {
+                memset(buf[k + p], 0, (size_t)c);
+                for (int i = 0; i < k; i++) {
+                    const uint8_t *row = mt + 256 * (size_t)j->rows[p * k + i];
+                    for (int64_t x = 0; x < c; x++) buf[k + p][x] ^= row[buf[i][x]];
+                }
+            }
+        } else {
+            job_t w = {j->kind, k, m, j->rows, j->mats, (const uint8_t *const *)buf, buf + k, 0, (size_t)c, 256 * 1024};
+            worker(&w);
+        }
+        for (int i = 0; i < k + m; i++) {
+            const uint64_t *w = (const uint64_t *)buf[i];
+            const uint64_t j0 = (uint64_t)off >> 3;
+            uint64_t s = 0;
+            for (int64_t x = 0; x < c / 8; x++) s += vd_mix(w[x], j0 + (uint64_t)x);
+            j->sums[i] += s;
+        }
+    }
+    for (int i = 0; i < k + m; i++) free(buf[i]);
+    return NULL;
+}
+
+int orc_volume_digests(int kind, int64_t dat_size, uint64_t seed, int k, int m, int64_t large, int64_t small,
+                       int threads, uint64_t *digests)
+{
+    if (kind == 0 && !g_ref_handle) return -1;
+    if (kind == 1 && !orc_cpu_has_gfni()) return -1;
+    if (k <= 0 || m <= 0 || k + m > ORC_MAX_SHARDS || dat_size < 0 || large <= 0 || small <= 0 || !digests ||
+        large % small || small % 8 || (kind != 0 && kind != 1 && kind != 2))
+        return -2;
+    if (threads < 1) threads = 1;
+    const int64_t shard_size = orc_expected_shard_size(dat_size, k, large, small);
+    int64_t chunk = small; /* divides every block; 64 KiB..1 MiB keeps a thread's 14 columns in L2 */
+    while (chunk > (1 << 18) && chunk % 2 == 0 && (chunk / 2) % 64 == 0) chunk /= 2;
+    uint8_t *gen = (uint8_t *)malloc((size_t)(k + m) * k);
+    orc_build_matrix(k, k + m, gen);
+    const uint8_t *rows = gen + (size_t)k * k;
+    uint64_t *mats = NULL;
+    if (kind == 1) {
+        mats = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)m * k);
+        for (int i = 0; i < m * k; i++) mats[i] = gfni_matrix(rows[i]);
+    }
+    vd_job_t *jobs = (vd_job_t *)calloc((size_t)threads, sizeof(vd_job_t));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (vd_job_t){.kind = kind, .k = k, .m = m, .id = t, .threads = threads, .dat_size = dat_size,
+                             .large = large, .small = small, .shard_size = shard_size, .chunk = chunk,
+                             .seed = seed, .rows = rows, .mats = mats};
+        pthread_create(&tids[t], NULL, vd_worker, &jobs[t]);
+    }
+    int rc = 0;
+    memset(digests, 0, sizeof(uint64_t) * (size_t)(k + m));
+    for (int t = 0; t < threads; t++) {
+        pthread_join(tids[t], NULL);
+        if (jobs[t].rc) rc = jobs[t].rc;
+        for (int i = 0; i < k + m; i++) digests[i] += jobs[t].sums[i];
+    }
+    free(jobs);
+    free(tids);
+    free(mats);
+    free(gen);
+    return rc;
+}

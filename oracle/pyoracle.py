@@ -65,6 +65,9 @@ def lib() -> C.CDLL:
         L.orc_cpu_bench.restype = C.c_double
         L.orc_cpu_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t]
 
+        L.orc_volume_digests.argtypes = [C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                         C.c_int, C.c_void_p]
+
         L.orc_generate_ec_files_simd.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]
 
         class Interval(C.Structure):
@@ -218,3 +221,38 @@ def generate_ec_files_simd(base: str, kind: int, buffer_size=256 * 1024, large=1
     if kind == 0 and not ref_available():
         return -38
     return lib().orc_generate_ec_files_simd(base.encode(), kind, buffer_size, large, small, k, m)
+
+
+def np_digest(arr: np.ndarray) -> int:
+    """The digest function of the device's swec_digest_kernel, restated in numpy:
+    Σ_j splitmix64_at(word_j, j) mod 2^64 over little-endian 8-byte words, tail zero-padded."""
+    pad = (-len(arr)) % 8
+    w = np.concatenate([arr, np.zeros(pad, dtype=np.uint8)]).view("<u8").astype(np.uint64)
+    with np.errstate(over="ignore"):
+        j = np.arange(len(w), dtype=np.uint64)
+        z = w + (j + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z.sum(dtype=np.uint64))
+
+
+def best_cpu_kind() -> int:
+    """0 = the reference's compiled C kernel (oracle/_ref), else 1 = GFNI port, else 2 = scalar tables."""
+    if ref_available():
+        return 0
+    return 1 if gfni_level() else 2
+
+
+def volume_digests(dat_size: int, seed: int, k=10, m=4, large=1 << 30, small=1 << 20, threads: int | None = None,
+                   kind: int | None = None) -> list[int]:
+    """Expected digests of all k+m shards of the seeded synthetic volume (orc_volume_digests): the whole
+    volume, regenerated and encoded on the CPU chunk by chunk, nothing held in memory."""
+    out = (C.c_uint64 * (k + m))()
+    kind = best_cpu_kind() if kind is None else kind
+    if kind == 0 and not ref_available():       # loads oracle/_ref on first use
+        raise RuntimeError("oracle/_ref not built")
+    rc = lib().orc_volume_digests(kind, dat_size, seed, k, m, large, small, threads or os.cpu_count() or 1, out)
+    if rc:
+        raise RuntimeError(f"orc_volume_digests rc={rc}")
+    return [int(v) for v in out]

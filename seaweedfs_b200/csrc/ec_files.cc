@@ -12,6 +12,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <libgen.h>
+#include <linux/falloc.h>
 #include <sys/stat.h>
 #include <sys/vfs.h>
 #include <unistd.h>
@@ -28,6 +29,7 @@
 #include <time.h>
 
 #include "engine.h"
+#include "io_pool.h"
 
 namespace swec {
 namespace {
@@ -46,13 +48,20 @@ std::string shard_ext(int idx) {  // ToExt, ec_encoder.go:106-108
     return b;
 }
 
-// posix_fallocate pays on disk filesystems (extents reserved once instead of 14 files growing 8 MiB at a time) and
-// costs on tmpfs, where it zero-fills every page that the writers overwrite a moment later.
+// Reserving extents pays on disk filesystems (once instead of 14 files growing 8 MiB at a time) and costs on tmpfs,
+// where it zero-fills every page that the writers overwrite a moment later.  The reservation must NOT change the
+// visible file size: DiskLocation.validateEcVolume (disk_location_ec.go:455-530) and rebuildEcFiles' equal-length
+// check recognise an interrupted encode by its short shards, so a killed run has to leave short files, not
+// full-size files of zeros — hence FALLOC_FL_KEEP_SIZE (reserve_extents), never posix_fallocate.
 bool worth_preallocating(int fd) {
     if (getenv("SWEC_NO_FALLOCATE")) return false;
     struct statfs fs;
     if (fstatfs(fd, &fs) != 0) return true;
     return fs.f_type != 0x01021994 /* TMPFS_MAGIC */ && fs.f_type != 0x858458f6 /* RAMFS_MAGIC */;
+}
+
+void reserve_extents(int fd, int64_t size) {  // best effort; the file's length stays what has been written
+    if (size > 0 && fallocate(fd, FALLOC_FL_KEEP_SIZE, 0, off_t(size)) != 0) errno = 0;
 }
 
 struct FdSet {
@@ -80,81 +89,6 @@ struct Slot {
     Item item;
 };
 
-// A few I/O threads shared by the reader and the writer side: every shard file is independent, so
-// the k preads of a stripe (and the k+m pwrites of a finished one) run concurrently.  One thread
-// doing them serially tops out near 1.5 GB/s even on RAM-backed files.
-class IoPool {
-  public:
-    explicit IoPool(size_t n) {
-        for (size_t i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
-    }
-    ~IoPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
-    // run fn(0..n-1) across the pool (the caller takes a share too); returns the first non-zero result
-    int parallel_for(int n, const std::function<int(int)>& fn) {
-        if (n <= 0) return 0;
-        Batch b;  // lives on this stack frame: nobody may touch it once finished == n has been observed
-        b.fn = &fn;
-        b.n = n;
-        std::unique_lock<std::mutex> lk(mu_);
-        batches_.push_back(&b);
-        cv_.notify_all();
-        work(&b, lk);
-        b.done_cv.wait(lk, [&] { return b.finished == b.n; });
-        batches_.erase(std::find(batches_.begin(), batches_.end(), &b));
-        return b.rc;
-    }
-
-  private:
-    struct Batch {
-        const std::function<int(int)>* fn = nullptr;
-        int n = 0, next = 0, finished = 0, rc = 0;
-        std::condition_variable done_cv;
-    };
-    // Called and returns with mu_ held.  A batch is only dereferenced while the lock has been held
-    // continuously since we last saw it unfinished (its owner cannot return without the lock).
-    void work(Batch* b, std::unique_lock<std::mutex>& lk) {
-        while (b->next < b->n) {
-            const int i = b->next++;
-            const std::function<int(int)>* fn = b->fn;
-            lk.unlock();
-            const int rc = (*fn)(i);
-            lk.lock();
-            if (rc && !b->rc) b->rc = rc;
-            if (++b->finished == b->n) {
-                b->done_cv.notify_all();
-                return;  // the owner may destroy the batch as soon as we release the lock
-            }
-        }
-    }
-    void loop() {
-        std::unique_lock<std::mutex> lk(mu_);
-        for (;;) {
-            Batch* b = nullptr;
-            cv_.wait(lk, [&] {
-                if (stop_) return true;
-                for (Batch* x : batches_)
-                    if (x->next < x->n) { b = x; return true; }
-                return false;
-            });
-            if (stop_) return;
-            if (b) work(b, lk);
-        }
-    }
-    std::vector<std::thread> threads_;
-    std::deque<Batch*> batches_;
-    std::mutex mu_;
-    std::condition_variable cv_;
-    bool stop_ = false;
-};
-
-// ---- end of IoPool (tests/test_iopool.py compiles the class above on its own under the sanitizers)
 
 // Staging rings outlive a call: pinning (mmap + mbind + cudaHostRegister) and un-pinning 3 x 14 x 8 MiB costs
 // 0.1-2 s per call (profiles/r01z_files_*), as much as the pipeline itself spends on an 8 GiB volume.  A volume
@@ -593,15 +527,15 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
     FilePipeline pipe(enc, rows, chunk);
     if ((rc = pipe.start())) return rc;
 
-    // The final shard size is known up front: reserve it — one I/O thread per file, because tmpfs
-    // zero-fills on fallocate — so the writers fill pages/extents that already exist instead of
+    // The final shard size is known up front: reserve its extents (visible length unchanged) — one I/O thread per
+    // file — so the writers fill pages/extents that already exist instead of
     // growing 14 files 8 MiB at a time under the filesystem's allocation lock (best effort).
     if (worth_preallocating(outs[0])) {
         const double tp = PipeStats::now();
         const int64_t shard_size = swec_expected_shard_size(st.st_size, k, large, small);
         if (shard_size > 0)
             pipe.parallel_for(total, [&](int i) -> int {
-                (void)posix_fallocate(outs[size_t(i)], 0, off_t(shard_size));
+                reserve_extents(outs[size_t(i)], shard_size);
                 return 0;
             });
         pipe.stats.prealloc += PipeStats::now() - tp;
@@ -727,11 +661,26 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     for (uint32_t id : missing) rebuilt[(*n_rebuilt)++] = id;
     if (missing.empty()) return SWEC_OK;
 
-    // pass 2: create the outputs — ec_encoder.go:182-193
+    // pass 2: create the outputs — ec_encoder.go:182-193.  Whatever goes wrong from here on, the caller gets no
+    // shard ids (the reference returns nil ids with the error) and no half-written output survives: a shard file
+    // that exists is taken for a present input by the next rebuild (findShardFile), so a partial one must not stay.
     std::vector<int> out(static_cast<size_t>(total), -1);
+    struct Undo {
+        const std::string& b;
+        const std::vector<uint32_t>& ids;
+        int* n_rebuilt;
+        size_t created = 0;
+        bool armed = true;
+        ~Undo() {
+            if (!armed) return;
+            for (size_t i = 0; i < created; i++) unlink((b + shard_ext(int(ids[i]))).c_str());
+            *n_rebuilt = 0;
+        }
+    } undo{b, missing, n_rebuilt};
     for (uint32_t id : missing) {
         const int fd = open((b + shard_ext(int(id))).c_str(), O_TRUNC | O_WRONLY | O_CREAT, 0644);
         if (fd < 0) return io_fail("create " + b + shard_ext(int(id)));
+        undo.created++;
         fds.fds.push_back(fd);
         out[id] = fd;
     }
@@ -761,7 +710,7 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     if ((rc = pipe.start())) return rc;
     if (todo > 0 && worth_preallocating(out[size_t(outs_idx[0])]))
         pipe.parallel_for(int(outs_idx.size()), [&](int r) -> int {
-            (void)posix_fallocate(out[size_t(outs_idx[size_t(r)])], 0, off_t(todo));
+            reserve_extents(out[size_t(outs_idx[size_t(r)])], todo);
             return 0;
         });
     for (int64_t o = 0; rc == SWEC_OK && o < todo; o += int64_t(chunk)) {
@@ -780,6 +729,7 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
         return rc;
     }
     if (ragged) return fail(SWEC_ERR_SHARD_SIZE, "ec shard size expected 1048576 actual " + std::to_string(size % mib));
+    undo.armed = false;
     return SWEC_OK;
 }
 

@@ -54,20 +54,34 @@ bool read_all(const std::string& path, std::vector<uint8_t>* out) {
     return true;
 }
 
+// Replaces `path` atomically: the bytes go to <path>.tmp.<pid>, which is renamed over the target.  A mounted
+// EcVolume maps .ecx MAP_SHARED (ec_volume.cc) and binary-searches the mapping; rewriting the same inode in place
+// (O_TRUNC) while it is mounted — ec.encode re-run on a mounted volume — would leave the search touching pages past
+// the new EOF: SIGBUS, which kills the whole volume server where the reference's ReadAt only returns an error.
+// With rename() existing mappings keep the old inode and its bytes until they are unmapped.
 bool write_all(const std::string& path, const std::vector<uint8_t>& data) {
-    const int fd = open(path.c_str(), O_TRUNC | O_CREAT | O_WRONLY, 0644);
+    const std::string tmp = path + ".tmp." + std::to_string(long(getpid()));
+    const int fd = open(tmp.c_str(), O_TRUNC | O_CREAT | O_WRONLY, 0644);
     if (fd < 0) return false;
     size_t put = 0;
     while (put < data.size()) {
         const ssize_t n = write(fd, data.data() + put, data.size() - put);
         if (n < 0) {
             if (errno == EINTR) continue;
+            const int keep = errno;
             close(fd);
+            unlink(tmp.c_str());
+            errno = keep;
             return false;
         }
         put += size_t(n);
     }
-    close(fd);
+    if (close(fd) != 0 || rename(tmp.c_str(), path.c_str()) != 0) {
+        const int keep = errno;
+        unlink(tmp.c_str());
+        errno = keep;
+        return false;
+    }
     return true;
 }
 

@@ -264,7 +264,8 @@ struct swec_ec_volume {
     size_t ecx_bytes = 0;
     std::string ecj;
     std::vector<uint64_t> deleted;  // ids of .ecj, sorted and unique: the reference's in-memory deletedNeedles set
-    int64_t ecj_size_seen = -1;
+    int64_t ecj_size_seen = -1, ecj_mtime_ns_seen = 0;
+    uint64_t ecj_inode_seen = 0;
     void index_journal() {
         deleted.clear();
         for (size_t off = 0; off + 8 <= ecj.size(); off += 8) {
@@ -287,12 +288,18 @@ struct swec_ec_volume {
 
 void swec_ec_volume::refresh_journal(bool force) {
     // the deletion journal grows while the volume is mounted (DeleteNeedleFromEcx appends to .ecj): pick up new
-    // entries when the file size moved — the reference keeps the same set in memory (ec_volume.go:351-384)
+    // entries when the file moved — size, mtime or inode, so a journal folded and re-created to the same length is
+    // seen too — the reference keeps the same set in memory (ec_volume.go:351-384)
     struct stat st;
-    const int64_t now = stat((index_base + ".ecj").c_str(), &st) == 0 ? int64_t(st.st_size) : 0;
-    if (!force && now == ecj_size_seen) return;
+    const bool have = stat((index_base + ".ecj").c_str(), &st) == 0;
+    const int64_t now = have ? int64_t(st.st_size) : 0;
+    const int64_t mt = have ? int64_t(st.st_mtim.tv_sec) * 1000000000ll + st.st_mtim.tv_nsec : 0;
+    const uint64_t ino = have ? uint64_t(st.st_ino) : 0;
+    if (!force && now == ecj_size_seen && mt == ecj_mtime_ns_seen && ino == ecj_inode_seen) return;
     if (now == 0 || !swec::slurp(index_base + ".ecj", &ecj)) ecj.clear();
     ecj_size_seen = now;
+    ecj_mtime_ns_seen = mt;
+    ecj_inode_seen = ino;
     index_journal();
 }
 
@@ -665,8 +672,13 @@ int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
     }
     if (found < 0) return SWEC_OK;                                   // already gone
     if (int32_t(be32(ex + found * 16 + 12)) < 0) return SWEC_OK;     // folded into .ecx by an earlier rebuild
+    // the in-memory set is authoritative between external changes of the file (refresh_journal notices those by
+    // size / mtime / inode): an O(log n) membership test and an 8-byte append per delete, like the reference's map
+    // check + append — not a re-read of the whole journal
+    v->refresh_journal();
+    if (std::binary_search(v->deleted.begin(), v->deleted.end(), needle_id)) return SWEC_OK;  // idempotent
     const std::string path = v->index_base + ".ecj";
-    const int fd = open(path.c_str(), O_RDWR | O_CREAT, 0644);
+    const int fd = open(path.c_str(), O_WRONLY | O_CREAT, 0644);
     if (fd < 0) return fail(SWEC_ERR_IO, "cannot open ec volume journal " + path + ": " + strerror(errno));
     struct stat st;
     if (fstat(fd, &st) != 0) {
@@ -674,20 +686,6 @@ int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
         close(fd);
         return fail(SWEC_ERR_IO, "stat ecj: " + std::string(strerror(e)));
     }
-    std::string cur(size_t(st.st_size), '\0');
-    if (st.st_size > 0 && pread(fd, &cur[0], cur.size(), 0) != ssize_t(cur.size())) {
-        const int e = errno;
-        close(fd);
-        return fail(SWEC_ERR_IO, "read ecj: " + std::string(strerror(e)));
-    }
-    for (size_t off = 0; off + 8 <= cur.size(); off += 8)
-        if (be64(reinterpret_cast<const uint8_t*>(cur.data()) + off) == needle_id) {  // idempotent
-            close(fd);
-            v->ecj = cur;
-            v->ecj_size_seen = st.st_size;
-            v->index_journal();
-            return SWEC_OK;
-        }
     uint8_t b[8];
     for (int i = 0; i < 8; i++) b[i] = uint8_t(needle_id >> (8 * (7 - i)));
     const bool ok = pwrite(fd, b, 8, st.st_size) == 8 && fsync(fd) == 0;
@@ -697,11 +695,18 @@ int swec_ec_volume_delete_needle(swec_ec_volume* v, uint64_t needle_id) {
         close(fd);
         return fail(SWEC_ERR_IO, "write ecj: " + std::string(strerror(e)));
     }
+    struct stat after;
+    const bool stat_ok = fstat(fd, &after) == 0;
     close(fd);
-    cur.append(reinterpret_cast<const char*>(b), 8);
-    v->ecj = cur;
-    v->ecj_size_seen = st.st_size + 8;
-    v->index_journal();
+    v->ecj.append(reinterpret_cast<const char*>(b), 8);
+    v->deleted.insert(std::upper_bound(v->deleted.begin(), v->deleted.end(), needle_id), needle_id);
+    if (stat_ok) {
+        v->ecj_size_seen = int64_t(after.st_size);
+        v->ecj_mtime_ns_seen = int64_t(after.st_mtim.tv_sec) * 1000000000ll + after.st_mtim.tv_nsec;
+        v->ecj_inode_seen = uint64_t(after.st_ino);
+    } else {
+        v->ecj_size_seen = -1;  // re-read on the next use
+    }
     return SWEC_OK;
 }
 

@@ -1,5 +1,6 @@
 // seaweedfs_b200/csrc/engine.cc — encoder object, matrix→kernel dispatch, host staging pipeline.
 #include "engine.h"
+#include "io_pool.h"
 
 #include <algorithm>
 #include <atomic>
@@ -69,6 +70,13 @@ static size_t env_size(const char* name, size_t dflt) {
 
 std::atomic<long> g_opt_stage_chunk{long(env_size("SWEC_STAGE_CHUNK", size_t(16) << 20))};
 std::atomic<long> g_opt_stage_slots{long(env_size("SWEC_STAGE_SLOTS", 3))};
+// Encoder-seam calls (swec_encode & co. on host buffers) are cut into at least this many pieces — never smaller
+// than host_min_chunk — so that the bounce copy / H2D of piece c+1, the kernel of piece c and the D2H / copy-back of
+// piece c-1 overlap INSIDE one call: the Go call sites hand over 256 KiB (encodeDataOneBatch) or 1 MiB
+// (rebuildEcFiles) per shard and wait for the result.
+std::atomic<long> g_opt_host_pieces{long(env_size("SWEC_HOST_PIECES", 4))};
+std::atomic<long> g_opt_host_min_chunk{long(env_size("SWEC_HOST_MIN_CHUNK", size_t(128) << 10))};
+std::atomic<long> g_opt_host_copy_threads{long(env_size("SWEC_HOST_COPY_THREADS", 0))};  // 0 = auto
 std::atomic<long> g_opt_jit_enabled{1};
 std::atomic<long> g_opt_jit_min_bytes{long(env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20))};
 
@@ -176,12 +184,17 @@ int swec_encoder_impl::ensure_slots(size_t chunk) {
     if (!slots.empty() && slot_chunk < chunk)
         chunk = std::min(std::max(chunk, 2 * slot_chunk), std::max(chunk, size_t(g_opt_stage_chunk.load())));
     chunk = std::max<size_t>(chunk, 64 * 1024);
-    for (auto& s : slots) {
-        if (s.stream) cudaStreamSynchronize(s.stream);
-        if (s.host) pinned_free(s.host);
-        if (s.dev) cudaFree(s.dev);
-        s.host = s.dev = nullptr;
-    }
+    auto release = [&] {  // the ring is all-or-nothing: a half-built one must never look "big enough"
+        slot_chunk = 0;
+        for (auto& s : slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.host) pinned_free(s.host);
+            if (s.dev) cudaFree(s.dev);
+            s.host = s.dev = nullptr;
+            s.busy = false;
+        }
+    };
+    release();
     for (size_t i = nslots; i < slots.size(); i++) {
         if (slots[i].done) cudaEventDestroy(slots[i].done);
         if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
@@ -190,10 +203,16 @@ int swec_encoder_impl::ensure_slots(size_t chunk) {
     const size_t streams = size_t(k) + 2 * size_t(m);
     for (auto& s : slots) {
         s.host = static_cast<uint8_t*>(pinned_alloc(device, streams * chunk));
-        if (!s.host) return fail(SWEC_ERR_NOMEM, "cannot allocate pinned staging memory");
-        SWEC_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk));
-        if (!s.stream) SWEC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        if (!s.done) SWEC_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        cudaError_t e = s.host ? cudaSuccess : cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk);
+        if (e == cudaSuccess && !s.stream) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess && !s.done) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            const bool no_host = !s.host;
+            release();
+            cudaGetLastError();
+            return no_host ? fail(SWEC_ERR_NOMEM, "cannot allocate pinned staging memory") : cuda_fail(e, "allocating the staging ring");
+        }
         s.busy = false;
     }
     slot_chunk = chunk;
@@ -344,12 +363,6 @@ int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8
 
 namespace {
 
-struct PendingCopy {
-    uint8_t* dst;
-    const uint8_t* src;
-    size_t len;
-};
-
 // Whatever way a host-path call ends, no DMA may still be aimed at the caller's buffers when it
 // returns ("nothing is retained after a call returns", include/swec.h).
 struct DrainSlotsOnExit {
@@ -378,6 +391,60 @@ bool is_pinned_or_device(const void* p, bool* is_device) {
     }
     *is_device = a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
     return a.type == cudaMemoryTypeHost || *is_device;
+}
+
+}  // namespace
+
+// ---- bounce copies between pageable caller memory and the pinned ring run across a few threads: one core moves
+// ~10 GB/s, a PCIe Gen5 x16 link 55 GB/s, so a single memcpy loop was the whole cost of an Encoder-level call from Go
+// heap memory (profiles/r01j_host_api_pageable.jsonl: 8.7 GB/s at 256 KiB per shard, below one GFNI core).
+namespace {
+
+struct CopyJob {
+    uint8_t* dst;
+    const uint8_t* src;
+    size_t len;
+};
+
+IoPool* host_pool() {  // leaked on purpose (threads must outlive static destructors); nullptr = copy inline
+    static IoPool* pool = [] () -> IoPool* {
+        long n = g_opt_host_copy_threads.load();
+        if (n <= 0) n = std::min<long>(8, std::max<long>(2, long(std::thread::hardware_concurrency()) / 8));
+        return n > 1 ? new IoPool(size_t(n - 1)) : nullptr;  // the caller takes a share too
+    }();
+    return pool;
+}
+
+void parallel_copy(const std::vector<CopyJob>& jobs) {
+    constexpr size_t kPiece = size_t(128) << 10, kInlineBelow = size_t(256) << 10;
+    size_t total = 0;
+    for (const CopyJob& j : jobs) total += j.len;
+    IoPool* pool = total > kInlineBelow ? host_pool() : nullptr;
+    if (!pool) {
+        for (const CopyJob& j : jobs) memcpy(j.dst, j.src, j.len);
+        return;
+    }
+    std::vector<CopyJob> pieces;
+    pieces.reserve(total / kPiece + jobs.size());
+    for (const CopyJob& j : jobs)
+        for (size_t o = 0; o < j.len; o += kPiece) pieces.push_back({j.dst + o, j.src + o, std::min(kPiece, j.len - o)});
+    const std::function<int(int)> one = [&](int i) {
+        memcpy(pieces[size_t(i)].dst, pieces[size_t(i)].src, pieces[size_t(i)].len);
+        return 0;
+    };
+    pool->parallel_for(int(pieces.size()), one);
+}
+
+// p[0..n) equally spaced (the k+m slices of ONE allocation, e.g. swec_alloc_pinned_for_device carved up by the caller)?
+bool constant_pitch(const uint8_t* const* p, int n, size_t min_pitch, size_t* pitch) {
+    if (n < 2) return false;
+    if (p[1] <= p[0]) return false;
+    const size_t d = size_t(p[1] - p[0]);
+    if (d < min_pitch) return false;
+    for (int i = 2; i < n; i++)
+        if (p[i] != p[0] + size_t(i) * d) return false;
+    *pitch = d;
+    return true;
 }
 
 }  // namespace
@@ -411,8 +478,14 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
         return SWEC_OK;
     }
 
+    // piece size: the call is cut into >= host_pieces pieces (>= host_min_chunk, <= stage_chunk each) travelling on
+    // the ring's slots, so that copies in, kernel and copies out of neighbouring pieces overlap inside this one call
     const size_t max_chunk = size_t(std::max(4096l, g_opt_stage_chunk.load()));
-    const size_t chunk = std::min(max_chunk, (n + 255) & ~size_t(255));
+    const size_t min_chunk = std::min(max_chunk, size_t(std::max(4096l, g_opt_host_min_chunk.load())));
+    const size_t pieces = size_t(std::max(1l, g_opt_host_pieces.load()));
+    size_t chunk = (((n + pieces - 1) / pieces) + 4095) & ~size_t(4095);
+    chunk = std::min(max_chunk, std::max(min_chunk, chunk));
+    chunk = std::min(chunk, (n + 255) & ~size_t(255));
     rc = e->ensure_slots(chunk);
     if (rc) return rc;
     const size_t stride = e->slot_chunk;  // per-stream pitch inside a slot (>= chunk)
@@ -425,21 +498,33 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
     }
     unsigned long long* const dev_bad = counter.p;
 
-    std::vector<std::vector<PendingCopy>> pending(e->slots.size());
+    std::vector<std::vector<CopyJob>> pending(e->slots.size());
     auto finish = [&](size_t si) -> int {
         StagingSlot& s = e->slots[si];
         if (!s.busy) return SWEC_OK;
         SWEC_CUDA(cudaEventSynchronize(s.done));
-        for (const PendingCopy& pc : pending[si]) memcpy(pc.dst, pc.src, pc.len);
+        parallel_copy(pending[si]);
         pending[si].clear();
         s.busy = false;
         return SWEC_OK;
     };
 
-    bool all_in_bounced = true, all_out_bounced = !check;
-    for (int i = 0; i < K; i++) all_in_bounced = all_in_bounced && !in_direct[size_t(i)];
-    for (int r = 0; r < R; r++) all_out_bounced = all_out_bounced && !out_direct[size_t(r)];
+    bool all_in_bounced = true, all_out_bounced = !check, all_in_direct = true, all_out_direct = !check;
+    for (int i = 0; i < K; i++) {
+        all_in_bounced = all_in_bounced && !in_direct[size_t(i)];
+        all_in_direct = all_in_direct && in_direct[size_t(i)];
+    }
+    for (int r = 0; r < R; r++) {
+        all_out_bounced = all_out_bounced && !out_direct[size_t(r)];
+        all_out_direct = all_out_direct && out_direct[size_t(r)];
+    }
+    // pinned callers whose k+m buffers are slices of one allocation: ONE strided DMA each way instead of k + m
+    size_t in_pitch = 0, out_pitch = 0;
+    const bool in_2d = all_in_direct && constant_pitch(in, K, n, &in_pitch);
+    const bool out_2d = all_out_direct && R > 1 && constant_pitch(out, R, n, &out_pitch);
+    const bool packed = all_in_bounced && all_out_bounced;
 
+    std::vector<CopyJob> bounce;
     size_t ci = 0;
     for (size_t off = 0; off < n; off += chunk, ci++) {
         const size_t si = ci % e->slots.size();
@@ -447,53 +532,62 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
         if ((rc = finish(si))) break;
         const size_t len = std::min(chunk, n - off);
         // Pageable callers (Go heap memory) bounce through the slot anyway, so pack the streams at a
-        // pitch that fits this call: one DMA in, one DMA out instead of k + m small ones.
-        const size_t pitch = all_in_bounced && all_out_bounced ? ((len + 255) & ~size_t(255)) : stride;
+        // pitch that fits this piece: one DMA in, one DMA out instead of k + m small ones.
+        const size_t pitch = packed ? ((len + 255) & ~size_t(255)) : stride;
         const uint8_t* din[SWEC_MAX_INPUTS];
         uint8_t* dout[SWEC_MAX_SHARDS];
+        bounce.clear();
         for (int i = 0; i < K; i++) {
-            uint8_t* d = s.dev + size_t(i) * pitch;
-            din[i] = d;
-            const uint8_t* src = in[i] + off;
-            if (!in_direct[size_t(i)]) {
-                memcpy(s.host + size_t(i) * pitch, src, len);
-                src = s.host + size_t(i) * pitch;
-            }
-            if (pitch == stride) SWEC_CUDA(cudaMemcpyAsync(d, src, len, cudaMemcpyDefault, s.stream));
+            din[i] = s.dev + size_t(i) * pitch;
+            if (!in_direct[size_t(i)]) bounce.push_back({s.host + size_t(i) * pitch, in[i] + off, len});
         }
-        if (pitch != stride)
+        parallel_copy(bounce);
+        if (packed) {
             SWEC_CUDA(cudaMemcpyAsync(s.dev, s.host, size_t(K - 1) * pitch + len, cudaMemcpyHostToDevice, s.stream));
+        } else if (in_2d) {
+            SWEC_CUDA(cudaMemcpy2DAsync(s.dev, pitch, in[0] + off, in_pitch, len, size_t(K), cudaMemcpyDefault, s.stream));
+        } else {
+            for (int i = 0; i < K; i++) {
+                const uint8_t* src = in_direct[size_t(i)] ? in[i] + off : s.host + size_t(i) * pitch;
+                SWEC_CUDA(cudaMemcpyAsync(s.dev + size_t(i) * pitch, src, len, cudaMemcpyDefault, s.stream));
+            }
+        }
         for (int r = 0; r < R; r++) dout[r] = s.dev + size_t(K + r) * pitch;
         if ((rc = e->apply(rows, din, dout, len, Layout{}, s.stream))) break;
-        if (pitch != stride) {
+        if (packed) {
             SWEC_CUDA(cudaMemcpyAsync(s.host + size_t(K) * pitch, dout[0], size_t(R - 1) * pitch + len,
                                       cudaMemcpyDeviceToHost, s.stream));
             for (int r = 0; r < R; r++) pending[si].push_back({out[r] + off, s.host + size_t(K + r) * pitch, len});
+        } else if (out_2d) {
+            SWEC_CUDA(cudaMemcpy2DAsync(out[0] + off, out_pitch, dout[0], pitch, len, size_t(R), cudaMemcpyDefault, s.stream));
         } else {
+            if (check) {  // bring the caller's copy of every row next to the computed one and compare in HBM
+                bounce.clear();
+                for (int r = 0; r < R; r++)
+                    if (!out_direct[size_t(r)]) bounce.push_back({s.host + size_t(K + r) * stride, out[r] + off, len});
+                parallel_copy(bounce);
+            }
             for (int r = 0; r < R; r++) {
                 if (check) {
-                    // bring the caller's copy of this row next to the computed one and compare in HBM
                     uint8_t* theirs = s.dev + size_t(K + R + r) * stride;
-                    const uint8_t* src = out[r] + off;
-                    if (!out_direct[size_t(r)]) {
-                        memcpy(s.host + size_t(K + r) * stride, src, len);
-                        src = s.host + size_t(K + r) * stride;
-                    }
+                    const uint8_t* src = out_direct[size_t(r)] ? out[r] + off : s.host + size_t(K + r) * stride;
                     SWEC_CUDA(cudaMemcpyAsync(theirs, src, len, cudaMemcpyDefault, s.stream));
                     SWEC_CUDA(launch_compare(dout[r], theirs, len, dev_bad, s.stream));
                 } else if (out_direct[size_t(r)]) {
                     SWEC_CUDA(cudaMemcpyAsync(out[r] + off, dout[r], len, cudaMemcpyDefault, s.stream));
                 } else {
-                    uint8_t* bounce = s.host + size_t(K + r) * stride;
-                    SWEC_CUDA(cudaMemcpyAsync(bounce, dout[r], len, cudaMemcpyDeviceToHost, s.stream));
-                    pending[si].push_back({out[r] + off, bounce, len});
+                    uint8_t* back = s.host + size_t(K + r) * stride;
+                    SWEC_CUDA(cudaMemcpyAsync(back, dout[r], len, cudaMemcpyDeviceToHost, s.stream));
+                    pending[si].push_back({out[r] + off, back, len});
                 }
             }
         }
         SWEC_CUDA(cudaEventRecord(s.done, s.stream));
         s.busy = true;
     }
-    for (size_t si = 0; si < e->slots.size(); si++) {
+    for (size_t i = 0; i < e->slots.size(); i++) {
+        // drain in submission order so that copy-backs of early pieces overlap the GPU work of late ones
+        const size_t si = (ci + i) % e->slots.size();
         const int rc2 = finish(si);
         if (!rc) rc = rc2;
     }
@@ -649,6 +743,8 @@ int swec_set_option(const char* name, long value) {
     else if (n == "ctas_per_sm" && value >= 0 && value <= 64) g_opt_ctas_per_sm = value;
     else if (n == "stage_chunk" && value >= 4096) g_opt_stage_chunk = (value + 255) & ~255l;
     else if (n == "stage_slots" && value >= 2 && value <= 16) g_opt_stage_slots = value;
+    else if (n == "host_pieces" && value >= 1 && value <= 64) g_opt_host_pieces = value;
+    else if (n == "host_min_chunk" && value >= 4096) g_opt_host_min_chunk = (value + 4095) & ~4095l;
     else if (n == "jit_min_bytes" && value >= 0) g_opt_jit_min_bytes = value;
     else if (n == "jit" && (value == 0 || value == 1)) g_opt_jit_enabled = value;
     else if (n == "xt_variant" && value >= 0 && value <= 3) g_opt_xt_variant = value;
@@ -1035,12 +1131,17 @@ int swec_encode_volume_device(swec_encoder* e, const void* dat_v, int64_t dat_si
         if (nfull && (rc = region(base, small, nfull, nlarge * large))) return rc;
         const int64_t tail = rem - nfull * small_row;
         if (tail > 0) {  // last row: bytes past EOF read as zero (ec_encoder.go:258-262)
-            uint8_t* scratch = nullptr;
-            SWEC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), size_t(small_row), s));
-            SWEC_CUDA(cudaMemsetAsync(scratch, 0, size_t(small_row), s));
-            SWEC_CUDA(cudaMemcpyAsync(scratch, base + nfull * small_row, size_t(tail), cudaMemcpyDeviceToDevice, s));
-            rc = region(scratch, small, 1, nlarge * large + nfull * small);
-            SWEC_CUDA(cudaFreeAsync(scratch, s));
+            struct Scratch {  // stream-ordered: freed after the work queued on s, on every exit path
+                uint8_t* p = nullptr;
+                cudaStream_t s;
+                ~Scratch() {
+                    if (p) cudaFreeAsync(p, s);
+                }
+            } scratch{nullptr, s};
+            SWEC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch.p), size_t(small_row), s));
+            SWEC_CUDA(cudaMemsetAsync(scratch.p, 0, size_t(small_row), s));
+            SWEC_CUDA(cudaMemcpyAsync(scratch.p, base + nfull * small_row, size_t(tail), cudaMemcpyDeviceToDevice, s));
+            rc = region(scratch.p, small, 1, nlarge * large + nfull * small);
             if (rc) return rc;
         }
     }

@@ -462,16 +462,9 @@ def test_custom_ratio_from_vif(cuda, swec, oracle, tmp_path):
 # ---------------------------------------------------------------- full-size properties (BASELINE configs 2-3)
 
 def np_digest(arr):
-    """Same function as swec_digest_kernel: Σ splitmix64(word_j + (j+1)·φ) mod 2^64."""
-    pad = (-len(arr)) % 8
-    w = np.concatenate([arr, np.zeros(pad, dtype=np.uint8)]).view("<u8").astype(np.uint64)
-    with np.errstate(over="ignore"):
-        j = np.arange(len(w), dtype=np.uint64)
-        z = w + (j + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-        return int(z.sum(dtype=np.uint64))
+    """Same function as swec_digest_kernel (restated in oracle/pyoracle.py)."""
+    from oracle import pyoracle
+    return pyoracle.np_digest(arr)
 
 
 def device_digest(swec, torch, t, nbytes=None):
@@ -498,8 +491,12 @@ def test_synth_and_digest_kernels_match_cpu(cuda, swec, oracle):
 @pytest.mark.parametrize("dat_size", [30 * (1 << 30), 30000 * (1 << 20) + 123_457])
 def test_full_volume_roundtrip_properties(cuda, swec, oracle, dat_size):
     """30 GiB (3 large rows) and the 30,000 MiB + ragged default-limit volume (2 large + 952+1 small
-    rows): encode on device; spot-check windows of every parity shard against the oracle; erase 4
-    shards (worst case: all data) → reconstruct → device digests equal the originals."""
+    rows): encode on device; the WHOLE of every parity shard (and of every extracted data shard) is
+    compared, through the device digest, with the digest the CPU oracle computes for the same seeded
+    volume walked through encodeDatFile's two-tier layout (oracle.volume_digests — every byte of the
+    BLOCKED large-row launch, the small-row launch and the zero-padded tail is covered, not windows);
+    windows are still compared byte for byte to localise a failure; then erase 4 shards (worst case:
+    all data) → reconstruct → device digests equal the oracle's."""
     torch = cuda
     ec = swec.erasure_coding
     G, M = 1 << 30, 1 << 20
@@ -536,6 +533,8 @@ def test_full_volume_roundtrip_properties(cuda, swec, oracle, dat_size):
         for p in range(4):
             assert (par[p][off:off + 4096].cpu().numpy() == want[p]).all(), (off, p)
     par_digest = [device_digest(swec, torch, p) for p in par]
+    expect = oracle.volume_digests(dat_size, SEED)            # all 14 shards, whole volume, CPU oracle
+    assert par_digest == expect[10:], "whole-volume parity digests differ from the CPU oracle"
 
     # worst case: data shards 0-3 erased; rebuild them from 4..13
     data_sh = [torch.empty(shard, dtype=torch.uint8, device="cuda") for _ in range(10)]
@@ -544,7 +543,8 @@ def test_full_volume_roundtrip_properties(cuda, swec, oracle, dat_size):
     torch.cuda.synchronize()
     del dat
     torch.cuda.empty_cache()
-    want_digest = [device_digest(swec, torch, data_sh[i]) for i in range(4)]
+    assert [device_digest(swec, torch, data_sh[i]) for i in range(10)] == expect[:10], "data shard layout"
+    want_digest = expect[:4]
     for i in range(4):
         data_sh[i].zero_()
     allsh = data_sh + par

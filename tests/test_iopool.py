@@ -1,4 +1,4 @@
-"""The file pipeline's I/O thread pool (ec_files.cc IoPool) hammered under ThreadSanitizer and
+"""The file pipeline's I/O thread pool (io_pool.h IoPool; also the bounce-copy pool of the Encoder seam) hammered under ThreadSanitizer and
 AddressSanitizer on the CPU: two submitters, thousands of tiny batches — the shape
 generateEcFiles("1", 50, 10000, 100) produces.  Regression test for a use-after-free of the
 stack-allocated batch record (seen as a segfault on the GPU box)."""
@@ -34,7 +34,7 @@ int main() {
 
 @pytest.mark.parametrize("sanitizer", ["thread", "address"])
 def test_iopool_under_sanitizers(tmp_path, sanitizer):
-    src = open(os.path.join(ROOT, "seaweedfs_b200", "csrc", "ec_files.cc")).read()
+    src = open(os.path.join(ROOT, "seaweedfs_b200", "csrc", "io_pool.h")).read()
     cls = src[src.index("class IoPool {"):src.index("// ---- end of IoPool")]
     head = "\n".join(f"#include <{h}>" for h in ("algorithm", "atomic", "condition_variable", "cstdio", "deque",
                                                   "functional", "mutex", "thread", "vector"))

@@ -179,3 +179,17 @@ def test_file_level_oracle(oracle, tmp_path):
 def test_synth_generators_agree(oracle):
     for off, n in ((0, 64), (5, 1000), (8 * 12345 + 3, 77)):
         assert (oracle.synth(off, n, 0x5EA3EED5F00DCAFE) == rn.synth(off, n, 0x5EA3EED5F00DCAFE)).all()
+
+
+@pytest.mark.parametrize("size", [0, 13, 40 << 20, (2 * 40 + 30 << 20) + 12345, (10 << 20) + 8, (50 << 20) - 1])
+def test_volume_digests_equal_digests_of_the_encoded_image(oracle, size):
+    """orc_volume_digests (the whole-volume checker of the 30 GiB GPU runs: nothing held in memory, columns
+    regenerated from the seeded generator through encodeDatFile's two-tier layout, ec_encoder.go:280-321) must give
+    the digests of the shards orc_encode_dat_image writes for the same volume — for the reference's own C kernel,
+    the GFNI port and the scalar tables alike."""
+    MIB = 1 << 20
+    dat = oracle.synth(0, size, 77)
+    want = [oracle.np_digest(w) for w in oracle.encode_dat_image(dat, large=4 * MIB, small=MIB)]
+    kinds = [2] + ([1] if oracle.gfni_level() else []) + ([0] if oracle.ref_available() else [])
+    for kind in kinds:
+        assert oracle.volume_digests(size, 77, large=4 * MIB, small=MIB, threads=3, kind=kind) == want, kind
