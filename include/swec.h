@@ -77,7 +77,8 @@ int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the dri
 void swec_shutdown(void);
 uint64_t swec_kernel_launches(void);          /* kernels this process has launched (all devices) */
 /* Tuning: "enc_threads" {128,256,512}, "enc_unroll" {1,2}, "ctas_per_sm" (0 = auto),
- * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "jit" {0,1},
+ * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "host_pieces" (a host-buffer call is cut into at
+ * least this many pipelined pieces), "host_min_chunk" (but none smaller than this many bytes per shard), "jit" {0,1},
  * "jit_min_bytes" (streams at least this long compile their kernel inline, shorter ones in the
  * background), "power_mode" {1 = always the boost-clock kernel variant (default), 2 = always the
  * low-power one, 0 = auto by the device's recent kernel time — a GPU that runs encode launches back to back
@@ -88,6 +89,12 @@ int swec_set_option(const char *name, long value);
  * loading it — needs no GPU.  Reports the cubin size and the generator's instruction statistics.  */
 int swec_debug_jit_compile(int r, int k, const uint8_t *rows, size_t *cubin_bytes, int *xtime_steps,
                            int *xor_ops);
+/* The decode-kernel cache (GPU analogue of the decode-matrix LRU, rse/src/core.rs:25,700-734), three tiers:
+ * `aot_matrices` reconstruct matrices compiled with the library (every single-shard loss of RS(10,4) and shards 0-3
+ * lost: no compile, no NVRTC, any stream length); an on-disk cubin cache shared by every process
+ * ($SWEC_CACHE_DIR, else $XDG_CACHE_HOME/swec, else ~/.cache/swec; SWEC_NO_DISK_CACHE=1 disables) whose hits are
+ * counted in `disk_cache_hits`; NVRTC for patterns never seen before (`nvrtc_compiles`).  Any pointer may be NULL. */
+int swec_jit_stats(uint64_t *nvrtc_compiles, uint64_t *disk_cache_hits, int *aot_matrices);
 
 /* ---- encoder = reedsolomon.New(dataShards, parityShards) ----------------------------------- */
 /* device < 0: host-side object only (matrix queries); compute calls then fail with NO_DEVICE.  */

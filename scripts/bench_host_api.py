@@ -1,51 +1,34 @@
 #!/usr/bin/env python
-"""scripts/bench_host_api.py — the Encoder-level C ABI on PAGEABLE host buffers at the batch sizes the
-Go code uses (256 KiB per shard in encodeDataOneBatch, 1 MiB in rebuildEcFiles, needle-sized degraded
-reads), next to one CPU thread of the reference arithmetic on the same buffers."""
+"""scripts/bench_host_api.py — sweep of the Encoder-level seam from host memory (bench.py's `host_api` leg) over the
+data paths the engine has for it: DMA ring vs zero-copy kernel, number of pipelined pieces per call, smallest piece.
+One JSON line per configuration; the 1-thread CPU arithmetic on the same buffers rides in every line."""
 import json
 import os
 import sys
-import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def rate(fn, min_s=0.5):
-    fn()
-    t0, n = time.perf_counter(), 0
-    while time.perf_counter() - t0 < min_s:
-        fn()
-        n += 1
-    return n / (time.perf_counter() - t0)
-
-
 def main():
     import seaweedfs_b200
-    from oracle import pyoracle as po
     from seaweedfs_b200 import erasure_coding as ec
+    import bench
+    L = seaweedfs_b200.lib()
     enc = ec.Encoder(10, 4, device=0)
-    rows = po.build_matrix(10, 14)[10:]
-    rng = np.random.default_rng(0)
-    for n in (4096, 65536, 256 * 1024, 1 << 20, 16 << 20):
-        shards = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)] + [np.zeros(n, dtype=np.uint8) for _ in range(4)]
-        r_enc = rate(lambda: enc.encode(shards))
-        holes = list(shards)
-
-        def recon():
-            holes[5] = None
-            enc.reconstruct_data(holes)
-        r_rec = rate(recon)
-        kind = 1 if po.gfni_level() else 0
-        outs = [np.zeros(n, dtype=np.uint8) for _ in range(4)]
-        r_cpu = rate(lambda: po.cpu_apply(kind, rows, shards[:10], outs, threads=1))
-        print(json.dumps({"shard_bytes": n, "encode_calls_per_s": round(r_enc, 1),
-                          "encode_input_GBps": round(r_enc * 10 * n / 1e9, 3),
-                          "reconstruct_data_calls_per_s": round(r_rec, 1),
-                          "reconstruct_input_GBps": round(r_rec * 10 * n / 1e9, 3),
-                          "cpu_1thread_input_GBps": round(r_cpu * 10 * n / 1e9, 3)}), flush=True)
+    sizes = (64 * 1024, 256 * 1024, 1 << 20, 4 << 20, 16 << 20)
+    configs = [(zc, pieces, minc) for zc in (0, 1) for pieces in (1, 2, 4) for minc in (64 << 10, 256 << 10)]
+    if len(sys.argv) > 1 and sys.argv[1] == "--quick":
+        configs = [(0, 4, 128 << 10), (1, 1, 128 << 10), (1, 2, 128 << 10), (1, 4, 128 << 10)]
+    for zc, pieces, minc in configs:
+        assert L.swec_set_option(b"host_zero_copy", zc) == 0
+        assert L.swec_set_option(b"host_pieces", pieces) == 0
+        assert L.swec_set_option(b"host_min_chunk", minc) == 0
+        leg = bench.host_api_leg(L, enc, 0, sizes=sizes, min_s=0.25)
+        row = {"zero_copy": zc, "pieces": pieces, "min_chunk": minc}
+        for n, r in leg["sizes"].items():
+            row[n] = {k.replace("_encode_GBps", "").replace("_GBps", ""): v for k, v in r.items() if k.endswith("GBps")}
+        print(json.dumps(row), flush=True)
 
 
 if __name__ == "__main__":

@@ -22,7 +22,7 @@ GEN = os.path.join(CSRC, "generated")
 LIB = os.path.join(HERE, "libswec.so")
 ROOT = os.path.dirname(HERE)
 
-SOURCES = ["kernels.cu", "engine.cc", "ec_files.cc", "ec_index.cc", "ec_volume.cc", "jit.cc", "codegen.cc", "gf256.cc"]
+SOURCES = ["kernels.cu", "aot_recon.cu", "engine.cc", "ec_files.cc", "ec_index.cc", "ec_volume.cc", "jit.cc", "codegen.cc", "gf256.cc"]
 HEADERS = ["apply_params.h", "device_common.cuh", "kernels.h", "engine.h", "gf256.h", "codegen.h", "io_pool.h",
            os.path.join(ROOT, "include", "swec.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -66,6 +66,12 @@ def generate() -> None:
     # the same combiner under a second name: kernels.cu binds it to the low-power multiply-by-2 step
     with open(os.path.join(GEN, "gen_rs10x4_encode_lp.inc"), "w") as f:
         f.write(out.replace("struct Rs10x4Encode ", "struct Rs10x4EncodeLP "))
+    # reconstruct matrices compiled ahead of time (aot_recon.cu): combiners + the matrix table they are found by
+    for emit, name in (("structs", "gen_aot_recon.inc"), ("keys", "gen_aot_recon_keys.inc")):
+        text = subprocess.run([tool, "--aot-recon", "10", "4", "--emit", emit], check=True,
+                              stdout=subprocess.PIPE, text=True).stdout
+        with open(os.path.join(GEN, name), "w") as f:
+            f.write(text)
     # JIT prelude: the two device headers, flattened (NVRTC cannot #include from disk)
     text = []
     for name in ("apply_params.h", "device_common.cuh"):
@@ -87,8 +93,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 return LIB
     generate()
     extra = os.environ.get("SWEC_EXTRA_NVCC_FLAGS", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", CSRC, "-I", GEN, "-shared", "-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
+    # one nvcc -c per source, in parallel (the two kernel files dominate), then one link step
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(GEN, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    common = [_nvcc()] + NVCC_FLAGS + extra + ["-I", CSRC, "-I", GEN]
+    objs = [os.path.join(objdir, os.path.splitext(src)[0] + ".o") for src in SOURCES]
+
+    def compile_one(pair):
+        src, obj = pair
+        cmd = common + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        _run(cmd)
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 2)) as ex:
+        list(ex.map(compile_one, zip(SOURCES, objs)))
+    cmd = common + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"]
     if verbose:
         print(" ".join(cmd))
     _run(cmd)

@@ -76,6 +76,13 @@ std::atomic<long> g_opt_stage_slots{long(env_size("SWEC_STAGE_SLOTS", 3))};
 // (rebuildEcFiles) per shard and wait for the result.
 std::atomic<long> g_opt_host_pieces{long(env_size("SWEC_HOST_PIECES", 4))};
 std::atomic<long> g_opt_host_min_chunk{long(env_size("SWEC_HOST_MIN_CHUNK", size_t(128) << 10))};
+// Zero-copy at the Encoder seam: the kernel reads the (mapped, pinned) host shards over PCIe itself and writes the
+// parity straight back to host memory — no staging in HBM, no DMA enqueue, one launch per piece.  What a short
+// synchronous call costs is API round trips, not bytes: 0 = never, 1 = whenever the buffers allow it,
+// 2 = auto: calls of at most host_zero_copy_max bytes per shard (bigger ones stream through the DMA ring).
+std::atomic<long> g_opt_host_zero_copy{long(env_size("SWEC_HOST_ZERO_COPY", 2))};
+std::atomic<long> g_opt_host_zero_copy_max{long(env_size("SWEC_HOST_ZERO_COPY_MAX", size_t(4) << 20))};
+std::atomic<long> g_opt_host_copy_spin_us{long(env_size("SWEC_HOST_COPY_SPIN_US", 200))};
 std::atomic<long> g_opt_host_copy_threads{long(env_size("SWEC_HOST_COPY_THREADS", 0))};  // 0 = auto
 std::atomic<long> g_opt_jit_enabled{1};
 std::atomic<long> g_opt_jit_min_bytes{long(env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20))};
@@ -114,7 +121,7 @@ void* pinned_alloc(int device, size_t bytes) {
             mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
             // MPOL_PREFERRED (1): stay on the GPU's node when it has room, never fail the allocation
             syscall(SYS_mbind, p, len, 1, mask, sizeof(mask) * 8, 0);
-            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
                 std::lock_guard<std::mutex> lk(g_pin_mu);
                 g_pin_mapped[p] = len;
                 return p;
@@ -124,7 +131,7 @@ void* pinned_alloc(int device, size_t bytes) {
         }
     }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
@@ -190,7 +197,7 @@ int swec_encoder_impl::ensure_slots(size_t chunk) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             if (s.host) pinned_free(s.host);
             if (s.dev) cudaFree(s.dev);
-            s.host = s.dev = nullptr;
+            s.host = s.dev = s.host_dev = nullptr;
             s.busy = false;
         }
     };
@@ -203,7 +210,12 @@ int swec_encoder_impl::ensure_slots(size_t chunk) {
     const size_t streams = size_t(k) + 2 * size_t(m);
     for (auto& s : slots) {
         s.host = static_cast<uint8_t*>(pinned_alloc(device, streams * chunk));
+        s.host_dev = nullptr;
         cudaError_t e = s.host ? cudaSuccess : cudaErrorMemoryAllocation;
+        if (e == cudaSuccess && cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.host_dev), s.host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            s.host_dev = nullptr;  // not mapped: the ring still works through DMA
+        }
         if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s.dev), streams * chunk);
         if (e == cudaSuccess && !s.stream) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess && !s.done) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
@@ -308,6 +320,12 @@ int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8
         if (is_rs10x4_parity(*this, rows)) {
             fill(p, 0, R, 0);
             SWEC_CUDA(launch_rs10x4_encode(p, layout.blocked, s));
+        } else if (const int aot = (rs10x4 && R <= 4 && K == 10 && g_opt_use_aot.load()) ? aot_recon_find(R, K, rows.v.data()) : -1;
+                   aot >= 0) {
+            // one of the reconstruct matrices compiled with the library (any single-shard loss, shards 0-3 lost):
+            // no compile, no threshold — needle-sized degraded reads take the Horner kernel too
+            fill(p, 0, R, 0);
+            SWEC_CUDA(launch_aot_recon(aot, p, layout.blocked, s));
         } else {
             // specialised (NVRTC) Horner kernel when the stream is long enough to pay for the
             // compile, or the kernel is already cached; otherwise shared-memory tables.
@@ -382,15 +400,20 @@ struct DeviceCounter {
     }
 };
 
-bool is_pinned_or_device(const void* p, bool* is_device) {
+// *gpu_ptr: the address the GPU uses for this memory (device memory: itself; mapped pinned host memory: its device
+// alias, the same value under unified addressing), nullptr if a kernel cannot reach it
+bool is_pinned_or_device(const void* p, bool* is_device, const void** gpu_ptr = nullptr) {
     cudaPointerAttributes a;
+    if (gpu_ptr) *gpu_ptr = nullptr;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
         *is_device = false;
         return false;
     }
     *is_device = a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-    return a.type == cudaMemoryTypeHost || *is_device;
+    const bool direct = a.type == cudaMemoryTypeHost || *is_device;
+    if (gpu_ptr && direct) *gpu_ptr = a.devicePointer;
+    return direct;
 }
 
 }  // namespace
@@ -410,7 +433,7 @@ IoPool* host_pool() {  // leaked on purpose (threads must outlive static destruc
     static IoPool* pool = [] () -> IoPool* {
         long n = g_opt_host_copy_threads.load();
         if (n <= 0) n = std::min<long>(8, std::max<long>(2, long(std::thread::hardware_concurrency()) / 8));
-        return n > 1 ? new IoPool(size_t(n - 1)) : nullptr;  // the caller takes a share too
+        return n > 1 ? new IoPool(size_t(n - 1), unsigned(g_opt_host_copy_spin_us.load())) : nullptr;  // the caller takes a share too
     }();
     return pool;
 }
@@ -460,19 +483,40 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
     if (rc) return rc;
 
     std::vector<char> in_direct(static_cast<size_t>(K), 0), out_direct(static_cast<size_t>(R), 0);
-    int ndev = 0;
+    const uint8_t* gin[SWEC_MAX_INPUTS];
+    uint8_t* gout[SWEC_MAX_SHARDS];
+    int ndev = 0, nreach = 0;
+    uintptr_t align = 0;
     for (int i = 0; i < K; i++) {
         bool dev;
-        in_direct[size_t(i)] = is_pinned_or_device(in[i], &dev);
+        const void* g = nullptr;
+        in_direct[size_t(i)] = is_pinned_or_device(in[i], &dev, &g);
+        gin[i] = static_cast<const uint8_t*>(g);
         ndev += dev;
+        nreach += g != nullptr;
+        align |= reinterpret_cast<uintptr_t>(g);
     }
     for (int r = 0; r < R; r++) {
         bool dev;
-        out_direct[size_t(r)] = is_pinned_or_device(out[r], &dev);
+        const void* g = nullptr;
+        out_direct[size_t(r)] = is_pinned_or_device(out[r], &dev, &g);
+        gout[r] = static_cast<uint8_t*>(const_cast<void*>(g));
         ndev += dev;
+        nreach += g != nullptr;
+        align |= reinterpret_cast<uintptr_t>(g);
     }
     if (ndev == K + R && !check) {  // everything already lives in HBM
         rc = e->apply(rows, in, out, n, Layout{}, e->stream);
+        if (rc) return rc;
+        SWEC_CUDA(cudaStreamSynchronize(e->stream));
+        return SWEC_OK;
+    }
+    const long zc_mode = g_opt_host_zero_copy.load();
+    const bool zero_copy = !check && (zc_mode == 1 || (zc_mode == 2 && n <= size_t(g_opt_host_zero_copy_max.load())));
+    if (zero_copy && nreach == K + R && (align & 15) == 0) {
+        // every buffer is mapped pinned (or device) memory: ONE launch reads the data shards over PCIe and writes
+        // the parity back; what a 256 KiB-per-shard Encode call costs is this launch and one stream synchronise
+        rc = e->apply(rows, gin, gout, n, Layout{}, e->stream);
         if (rc) return rc;
         SWEC_CUDA(cudaStreamSynchronize(e->stream));
         return SWEC_OK;
@@ -542,6 +586,17 @@ static int apply_host(swec_encoder_impl* e, const Matrix& rows, const uint8_t* c
             if (!in_direct[size_t(i)]) bounce.push_back({s.host + size_t(i) * pitch, in[i] + off, len});
         }
         parallel_copy(bounce);
+        if (packed && zero_copy && s.host_dev) {
+            // pageable caller, short call: the kernel works on the mapped ring itself (reads and writes cross PCIe
+            // inside the kernel), so a piece costs one launch instead of H2D + launch + D2H
+            for (int i = 0; i < K; i++) din[i] = s.host_dev + size_t(i) * pitch;
+            for (int r = 0; r < R; r++) dout[r] = s.host_dev + size_t(K + r) * pitch;
+            if ((rc = e->apply(rows, din, dout, len, Layout{}, s.stream))) break;
+            for (int r = 0; r < R; r++) pending[si].push_back({out[r] + off, s.host + size_t(K + r) * pitch, len});
+            SWEC_CUDA(cudaEventRecord(s.done, s.stream));
+            s.busy = true;
+            continue;
+        }
         if (packed) {
             SWEC_CUDA(cudaMemcpyAsync(s.dev, s.host, size_t(K - 1) * pitch + len, cudaMemcpyHostToDevice, s.stream));
         } else if (in_2d) {
@@ -728,6 +783,13 @@ void swec_shutdown(void) {
     file_pipeline_trim();
 }
 
+int swec_jit_stats(uint64_t* nvrtc_compiles, uint64_t* disk_cache_hits, int* aot_matrices) {
+    if (nvrtc_compiles) *nvrtc_compiles = jit_compile_count();
+    if (disk_cache_hits) *disk_cache_hits = jit_disk_hit_count();
+    if (aot_matrices) *aot_matrices = aot_recon_count();
+    return SWEC_OK;
+}
+
 int swec_debug_jit_compile(int r, int k, const uint8_t* rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
     if (r <= 0 || k <= 0 || k > SWEC_MAX_INPUTS || !rows) return fail(SWEC_ERR_INVALID_ARG, "bad matrix");
     Matrix m(r, k);
@@ -745,6 +807,8 @@ int swec_set_option(const char* name, long value) {
     else if (n == "stage_slots" && value >= 2 && value <= 16) g_opt_stage_slots = value;
     else if (n == "host_pieces" && value >= 1 && value <= 64) g_opt_host_pieces = value;
     else if (n == "host_min_chunk" && value >= 4096) g_opt_host_min_chunk = (value + 4095) & ~4095l;
+    else if (n == "host_zero_copy" && value >= 0 && value <= 2) g_opt_host_zero_copy = value;
+    else if (n == "host_zero_copy_max" && value >= 0) g_opt_host_zero_copy_max = value;
     else if (n == "jit_min_bytes" && value >= 0) g_opt_jit_min_bytes = value;
     else if (n == "jit" && (value == 0 || value == 1)) g_opt_jit_enabled = value;
     else if (n == "xt_variant" && value >= 0 && value <= 3) g_opt_xt_variant = value;
@@ -985,7 +1049,7 @@ int swec_alloc_pinned_shards(swec_encoder* const* encs, int n_encs, int n_shards
             for (int i = 0; i < n_shards && hi > lo; i++)  // MPOL_PREFERRED (1): never fails the allocation
                 syscall(SYS_mbind, static_cast<uint8_t*>(base) + size_t(i) * pitch + lo, hi - lo, 1, mask, sizeof(mask) * 8, 0);
         }
-    const cudaError_t e = cudaHostRegister(base, total, cudaHostRegisterPortable);
+    const cudaError_t e = cudaHostRegister(base, total, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) {
         munmap(base, total);
         return cuda_fail(e, "cudaHostRegister of the shard buffers");

@@ -49,8 +49,9 @@ struct DeviceTables {
 struct JitKernel;  // jit.cc
 
 struct StagingSlot {
-    uint8_t* host = nullptr;  // pinned, (k+m)*chunk
-    uint8_t* dev = nullptr;   // (k+m)*chunk
+    uint8_t* host = nullptr;      // pinned, (k+2m)*chunk
+    uint8_t* host_dev = nullptr;  // the same memory as the GPU addresses it (mapped pinned memory), or nullptr
+    uint8_t* dev = nullptr;       // (k+2m)*chunk
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     bool busy = false;
@@ -88,8 +89,10 @@ struct swec_encoder_impl {
     int get_tables(const Matrix& rows4, DeviceTables* out, cudaStream_t s);
 };
 
-// true when SWEC_NO_JIT is unset and NVRTC could be loaded
+// true when run-time specialised kernels can be had: NVRTC loaded (SWEC_NO_JIT unset), or the on-disk cubin cache is on
 bool jit_available();
+unsigned long long jit_compile_count();   // NVRTC compiles done by this process
+unsigned long long jit_disk_hit_count();  // kernels loaded from the on-disk cubin cache instead
 // Specialised Horner kernel for `rows` on the current device (compiled once per matrix/process).
 int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKernel>* out, bool wait = true, bool hot = false);
 int jit_debug_compile(const Matrix& rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops);

@@ -9,9 +9,20 @@
 //
 // NVRTC is dlopen'ed so that libswec.so itself has no load-time dependency beyond cudart; if it
 // cannot be found the engine uses the shared-memory table kernel instead (still on the GPU).
+//
+// The cache outlives the process: every compiled cubin is also written to an on-disk cache
+// ($SWEC_CACHE_DIR, else $XDG_CACHE_HOME/swec, else ~/.cache/swec; SWEC_NO_DISK_CACHE=1 turns it off), named by a
+// hash of the complete generated source, the target architecture and the CUDA runtime version.  A second process —
+// or a volume server without libnvrtc — loads a previously seen erasure pattern in a few milliseconds instead of
+// compiling for ~0.3 s.  The 15 most common patterns never get here at all: they are compiled with the library
+// (aot_recon.cu).
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
@@ -101,7 +112,7 @@ JitGlobal& G() {
     static JitGlobal* g = new JitGlobal;
     return *g;
 }
-constexpr int kHotUses = 2;        // a matrix is worth a background compile from its 2nd short use
+constexpr int kHotUses = 1;        // a matrix is worth a background compile from its first short use
 constexpr size_t kMaxQueued = 16;  // beyond that the table kernel keeps serving
 
 std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll, int variant);
@@ -139,8 +150,6 @@ void jit_stop_at_exit() {
 
 }  // namespace
 
-bool jit_available() { return nvrtc().ok; }
-
 void jit_shutdown() { jit_stop_at_exit(); }
 
 static std::vector<uint8_t> jit_key(const Matrix& rows, int threads, int unroll, int variant) {
@@ -153,11 +162,71 @@ bool jit_cached(swec_encoder_impl* enc, const Matrix& rows) {
     return enc->jit.count(jit_key(rows, int(g_opt_enc_threads.load()), int(g_opt_enc_unroll.load()), effective_xt_variant())) != 0;
 }
 
-// generate + NVRTC-compile the specialised kernels for `rows`; no CUDA context needed
-static int compile_cubin(const Matrix& rows, int threads, int unroll, int variant, std::vector<char>* cubin, CodegenStats* stats) {
-    Nvrtc& n = nvrtc();
-    if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
-    if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
+// ---- on-disk cubin cache -------------------------------------------------------------------------------------
+namespace {
+
+std::string disk_cache_dir() {
+    if (getenv("SWEC_NO_DISK_CACHE")) return "";
+    if (const char* d = getenv("SWEC_CACHE_DIR")) return *d ? std::string(d) : "";
+    if (const char* x = getenv("XDG_CACHE_HOME"))
+        if (*x) return std::string(x) + "/swec";
+    if (const char* h = getenv("HOME"))
+        if (*h) return std::string(h) + "/.cache/swec";
+    return "";
+}
+
+void mkdir_p(const std::string& dir) {
+    for (size_t i = 1; i <= dir.size(); i++)
+        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+}
+
+// 128 bits of FNV-1a (two different offsets) over the text that determines the cubin
+std::string cache_name(const std::string& src) {
+    int rt = 0;
+    cudaRuntimeGetVersion(&rt);
+    const std::string all = "swec-cubin-v1|sm_100a|rt" + std::to_string(rt) + "|" + src;
+    unsigned long long h1 = 0xcbf29ce484222325ull, h2 = 0x84222325cbf29ce4ull;
+    for (unsigned char c : all) {
+        h1 = (h1 ^ c) * 0x100000001b3ull;
+        h2 = (h2 ^ (c + 0x9e)) * 0x100000001b3ull;
+    }
+    char buf[64];
+    snprintf(buf, sizeof buf, "%016llx%016llx.cubin", h1, h2);
+    return buf;
+}
+
+bool read_file(const std::string& path, std::vector<char>* out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out->resize(n > 0 ? size_t(n) : 0);
+    const bool ok = n > 0 && fread(out->data(), 1, size_t(n), f) == size_t(n);
+    fclose(f);
+    return ok;
+}
+
+void write_file_atomic(const std::string& dir, const std::string& name, const std::vector<char>& data) {
+    mkdir_p(dir);
+    const std::string tmp = dir + "/." + name + "." + std::to_string(long(getpid())) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;  // the cache is best effort
+    const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    if (fclose(f) != 0 || !ok || rename(tmp.c_str(), (dir + "/" + name).c_str()) != 0) unlink(tmp.c_str());
+}
+
+std::atomic<unsigned long long> g_jit_compiles{0}, g_jit_disk_hits{0};
+
+}  // namespace
+
+unsigned long long jit_compile_count() { return g_jit_compiles.load(); }
+unsigned long long jit_disk_hit_count() { return g_jit_disk_hits.load(); }
+
+bool jit_available() { return nvrtc().ok || !disk_cache_dir().empty(); }
+
+// the complete source of the two specialised kernels for `rows` (also the identity of the cached cubin)
+static std::string jit_source(const Matrix& rows, int threads, int unroll, int variant, CodegenStats* stats) {
     const std::string T = std::to_string(threads), U = std::to_string(unroll);
     std::string src = "#define SWEC_XT_VARIANT " + std::to_string(variant) + "\n";
     src += kDeviceCommonSrc;
@@ -167,6 +236,25 @@ static int compile_cubin(const Matrix& rows, int threads, int unroll, int varian
         "    swec_horner_body<SwecJit, false, " + U + ">(p);\n}\n"
         "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_blocked(const __grid_constant__ SwecApplyParams p) {\n"
         "    swec_horner_body<SwecJit, true, " + U + ">(p);\n}\n";
+    return src;
+}
+
+// cubin for `rows`: from the disk cache when this exact source was compiled before (by any process), else NVRTC
+// (and into the cache).  No CUDA context needed.  *from_disk tells which.
+static int compile_cubin(const Matrix& rows, int threads, int unroll, int variant, std::vector<char>* cubin, CodegenStats* stats,
+                         bool* from_disk = nullptr, std::string* disk_path = nullptr) {
+    if (rows.rows > SWEC_MAX_OUTPUTS) return fail(SWEC_ERR_JIT, "too many output rows for one specialised kernel");
+    const std::string src = jit_source(rows, threads, unroll, variant, stats);
+    const std::string dir = disk_cache_dir(), name = dir.empty() ? "" : cache_name(src);
+    if (from_disk) *from_disk = false;
+    if (!dir.empty() && read_file(dir + "/" + name, cubin)) {
+        if (from_disk) *from_disk = true;
+        if (disk_path) *disk_path = dir + "/" + name;
+        g_jit_disk_hits++;
+        return SWEC_OK;
+    }
+    Nvrtc& n = nvrtc();
+    if (!n.ok) return fail(SWEC_ERR_JIT, "NVRTC not available and this matrix is not in the cubin cache");
     // one NVRTC compile at a time (the background worker and an inline caller may otherwise overlap)
     static std::mutex& compile_mu = *new std::mutex;
     std::lock_guard<std::mutex> compile_lock(compile_mu);
@@ -187,24 +275,34 @@ static int compile_cubin(const Matrix& rows, int threads, int unroll, int varian
     cubin->resize(cs);
     n.cubin(prog, cubin->data());
     n.destroy(&prog);
+    g_jit_compiles++;
+    if (!dir.empty()) write_file_atomic(dir, name, *cubin);
     return SWEC_OK;
 }
 
 namespace {
 std::shared_ptr<JitKernel> build_kernel(const Matrix& rows, int threads, int unroll, int variant) {
-    auto kernel = std::make_shared<JitKernel>();
-    kernel->threads = threads;
-    kernel->unroll = unroll;
-    std::vector<char> cubin;
-    if (compile_cubin(rows, threads, unroll, variant, &cubin, &kernel->stats) != SWEC_OK) return nullptr;
-    cudaError_t e = cudaLibraryLoadData(&kernel->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->flat, kernel->lib, "swec_jit_flat");
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->blocked, kernel->lib, "swec_jit_blocked");
-    if (e != cudaSuccess) {
+    for (int attempt = 0; attempt < 2; attempt++) {
+        auto kernel = std::make_shared<JitKernel>();
+        kernel->threads = threads;
+        kernel->unroll = unroll;
+        std::vector<char> cubin;
+        bool from_disk = false;
+        std::string disk_path;
+        if (compile_cubin(rows, threads, unroll, variant, &cubin, &kernel->stats, &from_disk, &disk_path) != SWEC_OK) return nullptr;
+        cudaError_t e = cudaLibraryLoadData(&kernel->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->flat, kernel->lib, "swec_jit_flat");
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&kernel->blocked, kernel->lib, "swec_jit_blocked");
+        if (e == cudaSuccess) return kernel;
+        cudaGetLastError();
+        if (from_disk && attempt == 0) {  // a truncated / foreign file in the cache: drop it and compile
+            unlink(disk_path.c_str());
+            continue;
+        }
         cuda_fail(e, "loading the specialised kernel");
         return nullptr;
     }
-    return kernel;
+    return nullptr;
 }
 
 }  // namespace
@@ -222,7 +320,7 @@ int jit_get(swec_encoder_impl* enc, const Matrix& rows, std::shared_ptr<JitKerne
         *out = local->second;
         return SWEC_OK;
     }
-    if (!nvrtc().ok) return fail(SWEC_ERR_JIT, "NVRTC not available");
+    if (!jit_available()) return fail(SWEC_ERR_JIT, "NVRTC not available and the cubin cache is off");
     JitGlobal& g = G();
     std::unique_lock<std::mutex> lock(g.mu);
     for (;;) {

@@ -7,6 +7,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# the library's on-disk cubin cache defaults to ~/.cache/swec; the test suite keeps its files inside the repo
+os.environ.setdefault("SWEC_CACHE_DIR", os.path.join(ROOT, ".pytest_cache", "swec_cubins"))
 
 
 def pytest_configure(config):

@@ -145,11 +145,12 @@ def test_argument_validation(swec, tmp_path):
 def test_set_option_validation(swec):
     L = swec.lib()
     for name, good, bad in ((b"power_mode", 2, 3), (b"xt_variant", 3, 4), (b"use_aot", 0, 2), (b"stage_slots", 4, 1),
-                            (b"enc_threads", 256, 300), (b"jit", 1, 5)):
+                            (b"enc_threads", 256, 300), (b"jit", 1, 5), (b"host_pieces", 2, 0), (b"host_min_chunk", 65536, 100)):
         assert L.swec_set_option(name, bad) == -1, name
         assert L.swec_set_option(name, good) == 0, name
     assert L.swec_set_option(b"no_such_option", 1) == -1 and L.swec_set_option(None, 1) == -1
-    for name, dflt in ((b"power_mode", 1), (b"xt_variant", 0), (b"use_aot", 1), (b"stage_slots", 3), (b"enc_threads", 512)):
+    for name, dflt in ((b"power_mode", 1), (b"xt_variant", 0), (b"use_aot", 1), (b"stage_slots", 3), (b"enc_threads", 512),
+                       (b"host_pieces", 4), (b"host_min_chunk", 128 << 10)):
         assert L.swec_set_option(name, dflt) == 0
 
 
@@ -234,6 +235,42 @@ def test_jit_source_compiles_for_sm100a_without_gpu(swec):
         assert rc == 0, L.swec_last_error()
         assert size.value > 1000 and steps.value <= 7 * rows.shape[0]
         print(rows.shape, size.value, steps.value, xors.value, round(time.perf_counter() - t0, 3))
+
+
+def test_cubin_disk_cache_and_aot_table(swec, tmp_path, monkeypatch):
+    """The decode-kernel cache outlives the process: a matrix compiled once is loaded from the on-disk cubin cache
+    the next time (no NVRTC compile), and the 15 most common reconstruct matrices are compiled with the library."""
+    import time
+    from oracle import rs_numpy as rn
+    L = swec.lib()
+    aot = C.c_int(0)
+    assert L.swec_jit_stats(None, None, C.byref(aot)) == 0 and aot.value == 15       # 14 single losses + shards 0-3
+    monkeypatch.setenv("SWEC_CACHE_DIR", str(tmp_path / "cubins"))
+    rows = np.ascontiguousarray(rn.fused_reconstruct_rows(10, 4, [i not in (3, 7, 12) for i in range(14)])[2], dtype=np.uint8)
+
+    def compile_once():
+        c0, h0 = C.c_uint64(0), C.c_uint64(0)
+        L.swec_jit_stats(C.byref(c0), C.byref(h0), None)
+        size = C.c_size_t(0)
+        t0 = time.perf_counter()
+        rc = L.swec_debug_jit_compile(rows.shape[0], rows.shape[1], rows.ctypes.data, C.byref(size), None, None)
+        dt = time.perf_counter() - t0
+        c1, h1 = C.c_uint64(0), C.c_uint64(0)
+        L.swec_jit_stats(C.byref(c1), C.byref(h1), None)
+        return rc, size.value, c1.value - c0.value, h1.value - h0.value, dt
+
+    rc, size, compiles, hits, _ = compile_once()
+    if rc == -8 and b"not available" in L.swec_last_error():
+        pytest.skip("NVRTC not installed here")
+    assert rc == 0 and (compiles, hits) == (1, 0)
+    files = list((tmp_path / "cubins").glob("*.cubin"))
+    assert len(files) == 1 and files[0].stat().st_size == size
+    rc, size2, compiles, hits, dt = compile_once()
+    assert rc == 0 and (compiles, hits) == (0, 1) and size2 == size and dt < 0.1, dt
+    # a truncated file in the cache is not fatal for loading paths; the debug entry just reports what it read
+    monkeypatch.setenv("SWEC_NO_DISK_CACHE", "1")
+    rc, _, compiles, hits, _ = compile_once()
+    assert rc == 0 and (compiles, hits) == (1, 0)
 
 
 def test_layout_arithmetic_fuzz_against_oracle(swec, oracle):

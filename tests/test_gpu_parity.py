@@ -90,6 +90,77 @@ def test_encode_adversarial_patterns(cuda, enc, oracle, kat, pattern):
         assert [[int(s[j]) for s in shards[10:]] for j in range(4)] == kat["K9"]["i_plus_j"]
 
 
+@pytest.mark.parametrize("zero_copy", [0, 1])
+@pytest.mark.parametrize("pieces", [1, 4])
+def test_host_seam_every_path_is_bit_exact(cuda, swec, oracle, zero_copy, pieces):
+    """The Encoder seam from host memory (swec_encode / swec_reconstruct / swec_verify, what a cgo
+    reedsolomon.Encoder calls — ec_encoder.go:265,360, store_ec.go:551) has four data paths: pageable memory
+    bounced through the pinned ring across the copy crew, pinned memory DMA'd in place (one strided DMA when the
+    shards are slices of one allocation), and for both the zero-copy variant where the kernel itself reads the host
+    shards over PCIe and writes the parity back.  Every one, cut into 1 or 4 pipelined pieces, with ragged and
+    unaligned lengths, must give the oracle's bytes and leave its neighbours untouched."""
+    import ctypes as C
+    L = swec.lib()
+    ec = swec.erasure_coding
+    assert L.swec_set_option(b"host_zero_copy", zero_copy) == 0
+    assert L.swec_set_option(b"host_pieces", pieces) == 0
+    assert L.swec_set_option(b"host_min_chunk", 4096) == 0
+    e = ec.Encoder(10, 4, device=0)
+    try:
+        for n, shift in ((1, 0), (15, 1), (4096 + 5, 0), (65536, 16), (256 * 1024, 0), (1 << 20, 0), ((1 << 20) + 4112, 3),
+                         (5 * (1 << 20) + 77, 0)):
+            rng = np.random.default_rng(n + shift)
+            data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+            want = oracle.encode(10, 4, data)
+            # pageable, each shard its own (possibly unaligned) view with guard bytes either side
+            backing = [np.full(n + 64, 0x5A, dtype=np.uint8) for _ in range(14)]
+            views = [b[shift + 16:shift + 16 + n] for b in backing]
+            for v, x in zip(views[:10], data):
+                v[:] = x
+            e.encode(views)
+            for v, w, b in zip(views[10:], want, backing[10:]):
+                assert (v == w).all(), (n, shift, "pageable")
+                assert (b[:shift + 16] == 0x5A).all() and (b[shift + 16 + n:] == 0x5A).all(), "stray write"
+            ok = C.c_int(0)
+            arr = (C.c_void_p * 14)(*[v.ctypes.data for v in views])
+            assert L.swec_verify(e._h, arr, n, C.byref(ok)) == 0 and ok.value == 1
+            lost = [views[i].copy() for i in (2, 11)]
+            holes = list(views)
+            views[2][:] = 0
+            views[11][:] = 0
+            holes[2] = holes[11] = None
+            e.reconstruct(holes)
+            assert (holes[2] == lost[0]).all() and (holes[11] == lost[1]).all(), (n, shift, "pageable reconstruct")
+            # pinned: the 14 slices of one allocation (constant pitch), pitch padded so that slices stay aligned
+            pitch = (n + shift + 255) & ~255
+            raw = L.swec_alloc_pinned_for_device(0, 14 * pitch + 64)
+            assert raw
+            try:
+                buf = np.ctypeslib.as_array(C.cast(raw, C.POINTER(C.c_uint8)), shape=(14 * pitch + 64,))
+                buf[:] = 0x5A
+                pinned = [buf[i * pitch + shift:i * pitch + shift + n] for i in range(14)]
+                for v, x in zip(pinned[:10], data):
+                    v[:] = x
+                e.encode(pinned)
+                for v, w in zip(pinned[10:], want):
+                    assert (v == w).all(), (n, shift, "pinned")
+                for i in range(14):
+                    assert (buf[i * pitch + shift + n:(i + 1) * pitch + (shift if i < 13 else 0)] == 0x5A).all(), "stray write"
+                keep = pinned[5].copy()
+                pinned[5][:] = 0
+                holes = list(pinned)
+                holes[5] = None
+                e.reconstruct_data(holes)
+                assert (holes[5] == keep).all(), (n, shift, "pinned reconstruct_data")
+            finally:
+                L.swec_free_pinned(raw)
+    finally:
+        e.close()
+        assert L.swec_set_option(b"host_zero_copy", 2) == 0
+        assert L.swec_set_option(b"host_pieces", 4) == 0
+        assert L.swec_set_option(b"host_min_chunk", 128 << 10) == 0
+
+
 @pytest.mark.parametrize("n", [1, 50, 256 * 1024, 5 * 1024 * 1024 + 77])
 def test_encode_host_pageable_and_pinned(cuda, swec, enc, oracle, n):
     """Encoder.Encode on host memory: 256 KiB is the reference's production batch (ec_encoder.go:68);

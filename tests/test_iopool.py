@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 MAIN = r"""
 int main() {
-    IoPool pool(8);
+    IoPool pool(8, SPIN_US);
     std::atomic<long> total{0};
     std::atomic<int> bad{0};
     auto user = [&](int seed) {
@@ -32,13 +32,14 @@ int main() {
 """
 
 
+@pytest.mark.parametrize("spin_us", [0, 50])
 @pytest.mark.parametrize("sanitizer", ["thread", "address"])
-def test_iopool_under_sanitizers(tmp_path, sanitizer):
+def test_iopool_under_sanitizers(tmp_path, sanitizer, spin_us):
     src = open(os.path.join(ROOT, "seaweedfs_b200", "csrc", "io_pool.h")).read()
     cls = src[src.index("class IoPool {"):src.index("// ---- end of IoPool")]
-    head = "\n".join(f"#include <{h}>" for h in ("algorithm", "atomic", "condition_variable", "cstdio", "deque",
+    head = "\n".join(f"#include <{h}>" for h in ("algorithm", "atomic", "chrono", "condition_variable", "cstdio", "deque",
                                                   "functional", "mutex", "thread", "vector"))
-    (tmp_path / "t.cc").write_text(head + "\n" + cls + MAIN)
+    (tmp_path / "t.cc").write_text(head + f"\n#define SPIN_US {spin_us}\n" + cls + MAIN)
     exe = str(tmp_path / "t")
     r = subprocess.run(["g++", "-O1", "-g", f"-fsanitize={sanitizer}", "-std=c++17", "-o", exe, str(tmp_path / "t.cc"),
                         "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
