@@ -546,3 +546,116 @@ int orc_volume_digests(int kind, int64_t dat_size, uint64_t seed, int k, int m, 
     free(gen);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * The CPU arm of the file-level comparison at ITS best schedule (bench infrastructure, not product): generateEcFiles
+ * with the same layout and the same shard bytes as ec_encoder.go:202-321, but scheduled the way the GPU pipeline is —
+ * many stripes in flight, large contiguous I/O, reads ∥ arithmetic ∥ writes — instead of the reference's serial
+ * 256 KiB loop.  Every thread owns every `threads`-th chunk of the shard space: k preads of its chunk of the .dat
+ * (layout offsets, zero past EOF), the SIMD encode (kind 0 = reference C kernel, 1 = GFNI port) on buffers that
+ * stay in its L2, k+m pwrites at the chunk's shard offset.  No cross-thread synchronisation at all.
+ * Answers "is the GPU file path fast because of the GPU or because of the schedule?".  0 or -errno. */
+typedef struct {
+    int kind, k, m, id, threads, dat, *outs;
+    int64_t dat_size, large, small, shard_size, chunk;
+    const uint8_t *rows;
+    const uint64_t *mats;
+    int rc;
+} gm_job_t;
+
+static void *gm_worker(void *arg)
+{
+    gm_job_t *j = (gm_job_t *)arg;
+    const int k = j->k, m = j->m;
+    const int64_t c = j->chunk;
+    uint8_t *buf[ORC_MAX_SHARDS];
+    for (int i = 0; i < k + m; i++)
+        if (posix_memalign((void **)&buf[i], 4096, (size_t)c)) { j->rc = -ENOMEM; return NULL; }
+    const int64_t large_row = j->large * k, small_row = j->small * k;
+    const int64_t nlarge = j->dat_size / large_row;
+    const int64_t nchunks = j->shard_size / c;
+    for (int64_t ci = j->id; ci < nchunks && j->rc == 0; ci += j->threads) {
+        const int64_t off = ci * c;
+        for (int i = 0; i < k; i++) {
+            int64_t src;
+            if (off < nlarge * j->large) src = (off / j->large) * large_row + i * j->large + off % j->large;
+            else {
+                const int64_t o2 = off - nlarge * j->large;
+                src = nlarge * large_row + (o2 / j->small) * small_row + i * j->small + o2 % j->small;
+            }
+            int64_t got = 0;
+            while (got < c) {
+                ssize_t n = pread(j->dat, buf[i] + got, (size_t)(c - got), (off_t)(src + got));
+                if (n < 0) { if (errno == EINTR) continue; j->rc = -errno; break; }
+                if (n == 0) break;
+                got += n;
+            }
+            if (got < c) memset(buf[i] + got, 0, (size_t)(c - got));
+        }
+        job_t w = {j->kind, k, m, j->rows, j->mats, (const uint8_t *const *)buf, buf + k, 0, (size_t)c, 256 * 1024};
+        worker(&w);
+        for (int i = 0; i < k + m && j->rc == 0; i++) {
+            int64_t put = 0;
+            while (put < c) {
+                ssize_t n = pwrite(j->outs[i], buf[i] + put, (size_t)(c - put), (off_t)(off + put));
+                if (n < 0) { if (errno == EINTR) continue; j->rc = -errno; break; }
+                put += n;
+            }
+        }
+    }
+    for (int i = 0; i < k + m; i++) free(buf[i]);
+    return NULL;
+}
+
+int orc_generate_ec_files_mt(const char *base, int kind, int threads, int64_t large, int64_t small, int k, int m)
+{
+    if (kind == 0 && !g_ref_handle) return -ENOSYS;
+    if (kind == 1 && !orc_cpu_has_gfni()) return -ENOSYS;
+    if (k <= 0 || m <= 0 || k + m > ORC_MAX_SHARDS || large <= 0 || small <= 0 || large % small || small % 4096) return -EINVAL;
+    if (threads < 1) threads = 1;
+    char path[4096];
+    snprintf(path, sizeof path, "%s.dat", base);
+    const int dat = open(path, O_RDONLY);
+    if (dat < 0) return -errno;
+    struct stat st;
+    fstat(dat, &st);
+    int outs[ORC_MAX_SHARDS], rc = 0;
+    for (int i = 0; i < k + m; i++) {
+        snprintf(path, sizeof path, "%s.ec%02d", base, i);
+        outs[i] = open(path, O_TRUNC | O_CREAT | O_WRONLY, 0644);
+        if (outs[i] < 0) rc = -errno;
+    }
+    uint8_t *gen = (uint8_t *)malloc((size_t)(k + m) * k);
+    orc_build_matrix(k, k + m, gen);
+    const uint8_t *rows = gen + (size_t)k * k;
+    uint64_t *mats = NULL;
+    if (kind == 1) {
+        mats = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)m * k);
+        for (int i = 0; i < m * k; i++) mats[i] = gfni_matrix(rows[i]);
+    }
+    int64_t chunk = small;
+    while (chunk > (1 << 20) && chunk % 2 == 0 && (chunk / 2) % 4096 == 0) chunk /= 2;
+    gm_job_t *jobs = (gm_job_t *)calloc((size_t)threads, sizeof(gm_job_t));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    if (rc == 0) {
+        for (int t = 0; t < threads; t++) {
+            jobs[t] = (gm_job_t){.kind = kind, .k = k, .m = m, .id = t, .threads = threads, .dat = dat, .outs = outs,
+                                 .dat_size = st.st_size, .large = large, .small = small,
+                                 .shard_size = orc_expected_shard_size(st.st_size, k, large, small), .chunk = chunk,
+                                 .rows = rows, .mats = mats};
+            pthread_create(&tids[t], NULL, gm_worker, &jobs[t]);
+        }
+        for (int t = 0; t < threads; t++) {
+            pthread_join(tids[t], NULL);
+            if (jobs[t].rc && !rc) rc = jobs[t].rc;
+        }
+    }
+    for (int i = 0; i < k + m; i++)
+        if (outs[i] >= 0) close(outs[i]);
+    close(dat);
+    free(jobs);
+    free(tids);
+    free(mats);
+    free(gen);
+    return rc;
+}

@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         L.orc_volume_digests.argtypes = [C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                          C.c_int, C.c_void_p]
 
+        L.orc_generate_ec_files_mt.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int]
         L.orc_generate_ec_files_simd.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]
 
         class Interval(C.Structure):
@@ -256,3 +257,14 @@ def volume_digests(dat_size: int, seed: int, k=10, m=4, large=1 << 30, small=1 <
     if rc:
         raise RuntimeError(f"orc_volume_digests rc={rc}")
     return [int(v) for v in out]
+
+
+def generate_ec_files_mt(base: str, kind: int | None = None, threads: int | None = None, large=1 << 30, small=1 << 20,
+                         k=10, m=4) -> int:
+    """generateEcFiles on the CPU at the GPU pipeline's schedule (orc_generate_ec_files_mt): the same-schedule CPU arm
+    of the file-level comparison.  kind None = the fastest arithmetic available (GFNI port, else reference C kernel)."""
+    if kind is None:
+        kind = 1 if gfni_level() else 0
+    if kind == 0 and not ref_available():
+        return -38
+    return lib().orc_generate_ec_files_mt(base.encode(), kind, threads or os.cpu_count() or 1, large, small, k, m)

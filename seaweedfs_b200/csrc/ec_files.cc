@@ -64,6 +64,17 @@ void reserve_extents(int fd, int64_t size) {  // best effort; the file's length 
     if (size > 0 && fallocate(fd, FALLOC_FL_KEEP_SIZE, 0, off_t(size)) != 0) errno = 0;
 }
 
+// a second descriptor on the same file with O_DIRECT, or -1 (tmpfs and friends refuse it; so may the caller's option)
+int open_direct(const std::string& path, int flags, bool wanted) {
+    if (!wanted) return -1;
+    const int fd = open(path.c_str(), flags | O_DIRECT);
+    if (fd < 0) errno = 0;
+    return fd;
+}
+inline bool direct_ok(int dfd, int64_t off, size_t len, const void* buf) {
+    return dfd >= 0 && ((uint64_t(off) | uint64_t(len) | reinterpret_cast<uintptr_t>(buf)) & 4095) == 0;
+}
+
 struct FdSet {
     std::vector<int> fds;
     ~FdSet() {
@@ -73,8 +84,9 @@ struct FdSet {
 };
 
 // fill bytes [dst_off, dst_off+len) of the slot's stream `stream` from fd@off (zero past EOF)
-struct ReadOp { int stream, fd; int64_t off; size_t dst_off, len; };
-struct WriteOp { int stream, fd; int64_t off; };           // drain stream `stream` of the slot to fd@off
+// dfd: the same file opened O_DIRECT (-1 = none): used when offset, length and buffer are all 4 KiB aligned
+struct ReadOp { int stream, fd; int64_t off; size_t dst_off, len; int dfd = -1; };
+struct WriteOp { int stream, fd; int64_t off; int dfd = -1; };  // drain stream `stream` of the slot to fd@off
 struct Item {
     size_t len = 0;
     std::vector<ReadOp> reads;
@@ -217,9 +229,13 @@ class FilePipeline {
             const ReadOp& r = item.reads[size_t(idx)];
             uint8_t* dst = s->host + size_t(r.stream) * chunk_ + r.dst_off;
             const size_t len = r.len;
+            // O_DIRECT: the device DMAs straight into the pinned slot; short counts only happen at EOF, where the
+            // remainder (unaligned now) continues on the buffered descriptor
+            const int fd0 = direct_ok(r.dfd, r.off, len, dst) ? r.dfd : r.fd;
             size_t got = 0;
             while (got < len) {
-                const ssize_t n = pread(r.fd, dst + got, len - got, off_t(r.off + int64_t(got)));
+                const int fd = (fd0 == r.dfd && direct_ok(r.dfd, r.off + int64_t(got), len - got, dst + got)) ? r.dfd : r.fd;
+                const ssize_t n = pread(fd, dst + got, len - got, off_t(r.off + int64_t(got)));
                 if (n < 0) {
                     if (errno == EINTR) continue;
                     const int rc = io_fail("pread");
@@ -387,7 +403,8 @@ class FilePipeline {
                     const uint8_t* src = s->host + size_t(w.stream) * chunk_;
                     size_t put = 0;
                     while (put < s->item.len) {
-                        const ssize_t n = pwrite(w.fd, src + put, s->item.len - put, off_t(w.off + int64_t(put)));
+                        const int fd = direct_ok(w.dfd, w.off + int64_t(put), s->item.len - put, src + put) ? w.dfd : w.fd;
+                        const ssize_t n = pwrite(fd, src + put, s->item.len - put, off_t(w.off + int64_t(put)));
                         if (n < 0) {
                             if (errno == EINTR) continue;
                             const int rc2 = io_fail("pwrite");
@@ -511,12 +528,17 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
     struct stat st;
     if (fstat(dat, &st) != 0) return io_fail("failed to stat dat file");
     const int total = k + m;
-    std::vector<int> outs(static_cast<size_t>(total), -1);
+    const long direct = g_opt_file_direct_io.load();
+    const int dat_d = open_direct(b + ".dat", O_RDONLY, direct & 1);
+    if (dat_d >= 0) fds.fds.push_back(dat_d);
+    std::vector<int> outs(static_cast<size_t>(total), -1), outs_d(static_cast<size_t>(total), -1);
     for (int i = 0; i < total; i++) {  // openEcFiles, ec_encoder.go:224-238
         const int fd = open((b + shard_ext(i)).c_str(), O_TRUNC | O_CREAT | O_WRONLY, 0644);
         if (fd < 0) return io_fail("failed to open file " + b + shard_ext(i));
         fds.fds.push_back(fd);
         outs[size_t(i)] = fd;
+        outs_d[size_t(i)] = open_direct(b + shard_ext(i), O_WRONLY, direct & 2);
+        if (outs_d[size_t(i)] >= 0) fds.fds.push_back(outs_d[size_t(i)]);
     }
 
     Matrix rows(m, k);
@@ -547,8 +569,8 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
         for (int64_t o = 0; o < block; o += int64_t(chunk)) {
             Item it;
             it.len = size_t(std::min<int64_t>(int64_t(chunk), block - o));
-            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + block * i + o, 0, it.len});
-            for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off + o});
+            for (int i = 0; i < k; i++) it.reads.push_back({i, dat, processed + block * i + o, 0, it.len, dat_d});
+            for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off + o, outs_d[size_t(i)]});
             const int r = pipe.submit(std::move(it));
             if (r) return r;
         }
@@ -577,8 +599,8 @@ int swec_generate_ec_files(const char* base, int64_t buffer_size, int64_t large,
         it.len = size_t(n * small);
         for (int64_t j = 0; j < n; j++)
             for (int i = 0; i < k; i++)
-                it.reads.push_back({i, dat, processed + j * small_row + int64_t(i) * small, size_t(j * small), size_t(small)});
-        for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off});
+                it.reads.push_back({i, dat, processed + j * small_row + int64_t(i) * small, size_t(j * small), size_t(small), dat_d});
+        for (int i = 0; i < total; i++) it.writes.push_back({i, outs[size_t(i)], shard_off, outs_d[size_t(i)]});
         rc = pipe.submit(std::move(it));
         shard_off += n * small;
         remaining -= n * small_row;
@@ -628,7 +650,8 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     std::string base_copy(b);
     const std::string base_name = basename(&base_copy[0]);
     FdSet fds;
-    std::vector<int> in(static_cast<size_t>(total), -1);
+    const long direct = g_opt_file_direct_io.load();
+    std::vector<int> in(static_cast<size_t>(total), -1), in_d(static_cast<size_t>(total), -1), out_d(static_cast<size_t>(total), -1);
     std::vector<uint8_t> present(static_cast<size_t>(total), 0);
     int npresent = 0;
     std::vector<uint32_t> missing;
@@ -652,6 +675,8 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
         if (fd < 0) return io_fail("open " + path);
         fds.fds.push_back(fd);
         in[size_t(i)] = fd;
+        in_d[size_t(i)] = open_direct(path, O_RDONLY, direct & 1);
+        if (in_d[size_t(i)] >= 0) fds.fds.push_back(in_d[size_t(i)]);
         present[size_t(i)] = 1;
         npresent++;
     }
@@ -683,6 +708,8 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
         undo.created++;
         fds.fds.push_back(fd);
         out[id] = fd;
+        out_d[id] = open_direct(b + shard_ext(int(id)), O_WRONLY, direct & 2);
+        if (out_d[id] >= 0) fds.fds.push_back(out_d[id]);
     }
 
     // rebuildEcFiles (ec_encoder.go:323-377): every present shard must have the same length; the
@@ -716,8 +743,9 @@ int swec_rebuild_ec_files(const char* base, const char* const* dirs, int ndirs, 
     for (int64_t o = 0; rc == SWEC_OK && o < todo; o += int64_t(chunk)) {
         Item it;
         it.len = size_t(std::min<int64_t>(int64_t(chunk), todo - o));
-        for (int i = 0; i < k; i++) it.reads.push_back({i, in[size_t(ins[size_t(i)])], o, 0, it.len});
-        for (size_t r = 0; r < outs_idx.size(); r++) it.writes.push_back({k + int(r), out[size_t(outs_idx[r])], o});
+        for (int i = 0; i < k; i++) it.reads.push_back({i, in[size_t(ins[size_t(i)])], o, 0, it.len, in_d[size_t(ins[size_t(i)])]});
+        for (size_t r = 0; r < outs_idx.size(); r++)
+            it.writes.push_back({k + int(r), out[size_t(outs_idx[r])], o, out_d[size_t(outs_idx[r])]});
         rc = pipe.submit(std::move(it));
     }
     const int rc2 = pipe.finish();

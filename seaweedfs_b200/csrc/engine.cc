@@ -84,6 +84,7 @@ std::atomic<long> g_opt_host_zero_copy{long(env_size("SWEC_HOST_ZERO_COPY", 2))}
 std::atomic<long> g_opt_host_zero_copy_max{long(env_size("SWEC_HOST_ZERO_COPY_MAX", size_t(4) << 20))};
 std::atomic<long> g_opt_host_copy_spin_us{long(env_size("SWEC_HOST_COPY_SPIN_US", 200))};
 std::atomic<long> g_opt_host_copy_threads{long(env_size("SWEC_HOST_COPY_THREADS", 0))};  // 0 = auto
+std::atomic<long> g_opt_file_direct_io{long(env_size("SWEC_FILE_DIRECT", 0)) & 3};
 std::atomic<long> g_opt_jit_enabled{1};
 std::atomic<long> g_opt_jit_min_bytes{long(env_size("SWEC_JIT_MIN_BYTES", size_t(64) << 20))};
 
@@ -110,13 +111,36 @@ int device_numa_node(int device) {
     return node;
 }
 
+// Pinned staging memory is carved out of 2 MiB-aligned anonymous mappings with MADV_HUGEPAGE: when several GPUs of one
+// socket DMA concurrently, every 4 KiB page is its own translation for the root complex / IOMMU, and the pages of a
+// huge page are physically contiguous, which DMA engines split less.  Best effort (the kernel may have THP off);
+// SWEC_NO_THP=1 keeps plain 4 KiB pages for A/B measurements.
+static void* map_aligned(size_t len, size_t* mapped_len) {
+    const size_t huge = size_t(2) << 20;
+    const bool thp = !getenv("SWEC_NO_THP") && len >= huge;
+    const size_t want = thp ? ((len + huge - 1) & ~(huge - 1)) : len;
+    const size_t span = thp ? want + huge : want;
+    uint8_t* raw = static_cast<uint8_t*>(mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (raw == MAP_FAILED) return nullptr;
+    uint8_t* p = raw;
+    if (thp) {
+        p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + huge - 1) & ~uintptr_t(huge - 1));
+        if (p > raw) munmap(raw, size_t(p - raw));
+        const size_t tail = size_t(raw + span - (p + want));
+        if (tail) munmap(p + want, tail);
+        madvise(p, want, MADV_HUGEPAGE);
+    }
+    *mapped_len = want;
+    return p;
+}
+
 void* pinned_alloc(int device, size_t bytes) {
     if (bytes == 0) return nullptr;
     const int node = getenv("SWEC_NO_NUMA") ? -1 : device_numa_node(device);
     if (node >= 0 && node < 1024) {
-        const size_t len = (bytes + 4095) & ~size_t(4095);
-        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-        if (p != MAP_FAILED) {
+        size_t len = (bytes + 4095) & ~size_t(4095);
+        void* p = map_aligned(len, &len);
+        if (p) {
             unsigned long mask[16] = {0};
             mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
             // MPOL_PREFERRED (1): stay on the GPU's node when it has room, never fail the allocation
@@ -807,6 +831,7 @@ int swec_set_option(const char* name, long value) {
     else if (n == "stage_slots" && value >= 2 && value <= 16) g_opt_stage_slots = value;
     else if (n == "host_pieces" && value >= 1 && value <= 64) g_opt_host_pieces = value;
     else if (n == "host_min_chunk" && value >= 4096) g_opt_host_min_chunk = (value + 4095) & ~4095l;
+    else if (n == "file_direct_io" && value >= 0 && value <= 3) g_opt_file_direct_io = value;
     else if (n == "host_zero_copy" && value >= 0 && value <= 2) g_opt_host_zero_copy = value;
     else if (n == "host_zero_copy_max" && value >= 0) g_opt_host_zero_copy_max = value;
     else if (n == "jit_min_bytes" && value >= 0) g_opt_jit_min_bytes = value;

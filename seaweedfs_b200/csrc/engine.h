@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -38,6 +39,10 @@ int device_numa_node(int device);
 
 // ecShardConfig.{dataShards,parityShards} of a .vif file (ec_files.cc); false when absent/unreadable
 bool read_vif_ratio(const std::string& path, int* ds, int* ps);
+// "file_direct_io" (SWEC_FILE_DIRECT): bit 0 = O_DIRECT reads of the .dat / shard inputs straight into the pinned
+// ring, bit 1 = O_DIRECT writes of the shard outputs — the page cache is bypassed both ways (disk-backed volumes only;
+// files that refuse O_DIRECT, tmpfs for one, and unaligned pieces silently take the buffered descriptor)
+extern std::atomic<long> g_opt_file_direct_io;
 void file_pipeline_trim();  // ec_files.cc: release staging rings parked between file-level calls
 
 // device-resident multiply tables of one R×K matrix (R ≤ 4)
