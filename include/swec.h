@@ -80,9 +80,12 @@ uint64_t swec_kernel_launches(void);          /* kernels this process has launch
  * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "host_pieces" (a host-buffer call is cut into at
  * least this many pipelined pieces), "host_min_chunk" (but none smaller than this many bytes per shard), "jit" {0,1},
  * "jit_min_bytes" (streams at least this long compile their kernel inline, shorter ones in the
- * background), "power_mode" {1 = always the boost-clock kernel variant (default), 2 = always the
- * low-power one, 0 = auto by the device's recent kernel time — a GPU that runs encode launches back to back
- * for more than ~0.3 s sits on its power cap, where the variant with fewer instructions is 4-5 % faster}.  Measurement knobs: "xt_variant" {0..3} (instruction mix of run-time specialised kernels,
+ * background), "power_mode" {0 = auto by the device's recent kernel time (default) — a GPU that runs
+ * encode launches back to back for more than ~0.4 s sits on its power cap, where the variant with fewer instructions is
+ * 4-5 % faster; 1 = always the boost-clock kernel variant, 2 = always the low-power one}, "host_zero_copy" {0,1,2 = auto:
+ * host-buffer calls of at most "host_zero_copy_max" bytes per shard run the kernel directly on the (mapped, pinned) host
+ * memory over PCIe instead of staging through HBM}, "file_direct_io" {bit 0: O_DIRECT reads, bit 1: O_DIRECT writes in
+ * the file-level entry points}.  Measurement knobs: "xt_variant" {0..3} (instruction mix of run-time specialised kernels,
  * device_common.cuh), "use_aot" {0,1} (0: RS(10,4) encode is specialised at run time like any matrix).     */
 int swec_set_option(const char *name, long value);
 /* Diagnostics: generate and NVRTC-compile (sm_100a) the specialised kernel for an r×k matrix without
@@ -163,6 +166,13 @@ int swec_encode_volume_device(swec_encoder *enc, const void *dat, int64_t dat_si
 int swec_extract_data_shard_device(swec_encoder *enc, const void *dat, int64_t dat_size,
                                    int64_t large_block, int64_t small_block, int shard_id,
                                    void *shard_out, void *stream);
+/* WriteDatFile on device memory (weed/storage/erasure_coding/ec_decoder.go:176-223, the body of ec.decode): the k data
+ * shards, each swec_expected_shard_size() bytes in HBM (as read from .ec00-.ec09, or as swec_reconstruct_device just
+ * rebuilt them), are un-striped into the dat_size bytes of the volume image — rows of k large blocks while at least one
+ * full large row remains, then rows of k small blocks, the zero padding of the last row dropped.  Exact inverse of
+ * swec_extract_data_shard_device; k strided device-to-device copies per region, asynchronous on `stream`.           */
+int swec_write_dat_device(swec_encoder *enc, const void *const *data_shards, int64_t dat_size,
+                          int64_t large_block, int64_t small_block, void *dat_out, void *stream);
 int swec_stream_synchronize(swec_encoder *enc, void *stream);
 
 /* ---- file level: .dat → .ec00…, missing .ecNN ← the others, .ec00–.ec09 → .dat -------------- */

@@ -122,40 +122,6 @@ func shardLen(shards [][]byte) (int, error) {
 	return n, nil
 }
 
-// ---- pinned batch buffers ---------------------------------------------------------------------------------
-// runtime.Pinner only stops the Go GC from moving a slice; to CUDA such memory is PAGEABLE, so every Encode /
-// Reconstruct on it bounces through the library's pinned ring (a memcpy per shard each way).  The batch buffers of
-// the two file loops are allocated once per volume and reused for every batch, so they are the place to hand the
-// library memory it can DMA — or read from the kernel — directly:
-//
-//   encodeDatFile      ec_encoder.go:289-292   buffers[i] = make([]byte, bufferSize)   ×TotalShards
-//   rebuildEcFiles     ec_encoder.go:330-335   buffers[i] = make([]byte, ErasureCodingSmallBlockSize) ×TotalShards
-//   recoverOneRemoteEcShardInterval  store_ec.go:493-500   bufs[i] = make([]byte, len(buf))  (per degraded read)
-//
-// become   buffers, release := swecAllocShardBuffers(ctx.Total(), bufferSize); defer release()
-//
-// The n slices are cut from ONE pinned, GPU-mapped allocation on the GPU's NUMA node at a constant pitch: the library
-// recognises that shape and moves all k inputs (and all m outputs) with one strided DMA each way, or — for calls up to
-// 4 MiB per shard — runs the kernel directly on the host memory over PCIe (include/swec.h "host_zero_copy").
-// The memory is C memory: no Pinner, no cgo pointer-passing rules, and the slices must not outlive release().
-func swecAllocShardBuffers(n int, shardLen int) (bufs [][]byte, release func()) {
-	pitch := (shardLen + 4095) &^ 4095
-	dev := swecPickDevice()
-	base := C.swec_alloc_pinned_for_device(dev, C.size_t(n*pitch))
-	if base == nil { // no GPU / out of pinned memory: plain Go memory still works (pageable path)
-		bufs = make([][]byte, n)
-		for i := range bufs {
-			bufs[i] = make([]byte, shardLen)
-		}
-		return bufs, func() {}
-	}
-	bufs = make([][]byte, n)
-	for i := range bufs {
-		bufs[i] = unsafe.Slice((*byte)(unsafe.Add(base, i*pitch)), shardLen)
-	}
-	return bufs, func() { C.swec_free_pinned(base) }
-}
-
 // Encode: parity slices overwritten in place, data untouched (ec_encoder.go:265).
 func (e *swecEncoder) Encode(shards [][]byte) error {
 	if len(shards) != e.data+e.par {
@@ -412,4 +378,38 @@ func (v *swecEcVolume) ReadNeedles(ids []uint64, capacity int) ([][]byte, []erro
 // DeleteNeedleFromEcx: journal append (ec_volume_delete.go:28-93).
 func (v *swecEcVolume) DeleteNeedleFromEcx(id uint64) error {
 	return swecCall(func() C.int { return C.swec_ec_volume_delete_needle(v.h, C.uint64_t(id)) })
+}
+
+// ---- pinned batch buffers ---------------------------------------------------------------------------------
+// runtime.Pinner only stops the Go GC from moving a slice; to CUDA such memory is PAGEABLE, so every Encode /
+// Reconstruct on it bounces through the library's pinned ring (a memcpy per shard each way).  The batch buffers of
+// the two file loops are allocated once per volume and reused for every batch, so they are the place to hand the
+// library memory it can DMA — or read from the kernel — directly:
+//
+//   encodeDatFile      ec_encoder.go:289-292   buffers[i] = make([]byte, bufferSize)   ×TotalShards
+//   rebuildEcFiles     ec_encoder.go:330-335   buffers[i] = make([]byte, ErasureCodingSmallBlockSize) ×TotalShards
+//   recoverOneRemoteEcShardInterval  store_ec.go:493-500   bufs[i] = make([]byte, len(buf))  (per degraded read)
+//
+// become   buffers, release := swecAllocShardBuffers(ctx.Total(), bufferSize); defer release()
+//
+// The n slices are cut from ONE pinned, GPU-mapped allocation on the GPU's NUMA node at a constant pitch: the library
+// recognises that shape and moves all k inputs (and all m outputs) with one strided DMA each way, or — for calls up to
+// 4 MiB per shard — runs the kernel directly on the host memory over PCIe (include/swec.h "host_zero_copy").
+// The memory is C memory: no Pinner, no cgo pointer-passing rules, and the slices must not outlive release().
+func swecAllocShardBuffers(n int, shardLen int) (bufs [][]byte, release func()) {
+	pitch := (shardLen + 4095) &^ 4095
+	dev := swecPickDevice()
+	base := C.swec_alloc_pinned_for_device(dev, C.size_t(n*pitch))
+	if base == nil { // no GPU / out of pinned memory: plain Go memory still works (pageable path)
+		bufs = make([][]byte, n)
+		for i := range bufs {
+			bufs[i] = make([]byte, shardLen)
+		}
+		return bufs, func() {}
+	}
+	bufs = make([][]byte, n)
+	for i := range bufs {
+		bufs[i] = unsafe.Slice((*byte)(unsafe.Add(base, i*pitch)), shardLen)
+	}
+	return bufs, func() { C.swec_free_pinned(base) }
 }

@@ -73,6 +73,7 @@ PROTOTYPES = {
                                             C.c_void_p, C.c_void_p]),
     "swec_extract_data_shard_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                                  C.c_int, C.c_void_p, C.c_void_p]),
+    "swec_write_dat_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "swec_stream_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "swec_write_ec_files": (C.c_int, [C.c_char_p, C.c_int]),
     "swec_generate_ec_files": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]),

@@ -38,9 +38,10 @@ namespace swec {
 
 constexpr int kAotThreads = 512, kAotUnroll = 2;  // the measured-best shape of the encode kernel
 
-template <class Combiner, bool BLOCKED>
+// flat layout only: reconstruct works on whole shard streams (the blocked layout is the .dat striping, an encode matter)
+template <class Combiner>
 __global__ void __launch_bounds__(kAotThreads) swec_aot_recon(const __grid_constant__ SwecApplyParams p) {
-    swec_horner_body<Combiner, BLOCKED, kAotUnroll>(p);
+    swec_horner_body<Combiner, false, kAotUnroll>(p);
 }
 
 int aot_recon_find(int r, int k, const unsigned char* coef) {
@@ -52,7 +53,7 @@ int aot_recon_find(int r, int k, const unsigned char* coef) {
 
 int aot_recon_count() { return SWEC_AOT_RECON_COUNT; }
 
-cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, bool blocked, cudaStream_t s) {
+cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, cudaStream_t s) {
     if (p.nvec == 0) return cudaSuccess;
     if (idx < 0 || idx >= SWEC_AOT_RECON_COUNT) return cudaErrorInvalidValue;
     int sms = 148, dev = 0;
@@ -67,15 +68,10 @@ cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, bool blocked, cu
     note_kernel_work(double(p.nvec) * 16.0 * double(kAotReconKeys[idx].k + kAotReconKeys[idx].r) / 6.2e9 * 1e3);
     g_kernel_launches++;
     switch (idx) {
-#define SWEC_AOT_CASE(I)                                                                                            \
-    case I:                                                                                                         \
-        if (lp) {                                                                                                   \
-            if (blocked) swec_aot_recon<swec_aot_lowpower::SwecAotRecon##I, true><<<grid, kAotThreads, 0, s>>>(p);    \
-            else swec_aot_recon<swec_aot_lowpower::SwecAotRecon##I, false><<<grid, kAotThreads, 0, s>>>(p);           \
-        } else {                                                                                                    \
-            if (blocked) swec_aot_recon<swec_aot_boost::SwecAotRecon##I, true><<<grid, kAotThreads, 0, s>>>(p);       \
-            else swec_aot_recon<swec_aot_boost::SwecAotRecon##I, false><<<grid, kAotThreads, 0, s>>>(p);              \
-        }                                                                                                           \
+#define SWEC_AOT_CASE(I)                                                                              \
+    case I:                                                                                           \
+        if (lp) swec_aot_recon<swec_aot_lowpower::SwecAotRecon##I><<<grid, kAotThreads, 0, s>>>(p);     \
+        else swec_aot_recon<swec_aot_boost::SwecAotRecon##I><<<grid, kAotThreads, 0, s>>>(p);           \
         break;
         SWEC_AOT_RECON_FOREACH(SWEC_AOT_CASE)
 #undef SWEC_AOT_CASE

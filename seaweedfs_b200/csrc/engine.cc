@@ -75,13 +75,15 @@ std::atomic<long> g_opt_stage_slots{long(env_size("SWEC_STAGE_SLOTS", 3))};
 // piece c-1 overlap INSIDE one call: the Go call sites hand over 256 KiB (encodeDataOneBatch) or 1 MiB
 // (rebuildEcFiles) per shard and wait for the result.
 std::atomic<long> g_opt_host_pieces{long(env_size("SWEC_HOST_PIECES", 4))};
-std::atomic<long> g_opt_host_min_chunk{long(env_size("SWEC_HOST_MIN_CHUNK", size_t(128) << 10))};
+std::atomic<long> g_opt_host_min_chunk{long(env_size("SWEC_HOST_MIN_CHUNK", size_t(256) << 10))};
 // Zero-copy at the Encoder seam: the kernel reads the (mapped, pinned) host shards over PCIe itself and writes the
 // parity straight back to host memory — no staging in HBM, no DMA enqueue, one launch per piece.  What a short
 // synchronous call costs is API round trips, not bytes: 0 = never, 1 = whenever the buffers allow it,
 // 2 = auto: calls of at most host_zero_copy_max bytes per shard (bigger ones stream through the DMA ring).
+// Measured (profiles/r02b_host_api_sweep.jsonl): zero-copy wins up to ~1-2 MiB per shard (pinned 256 KiB: 35.8 vs 28.4 GB/s,
+// ReconstructData at 1 MiB: 47 vs 27-38), the 4-piece DMA ring from 4 MiB (46.9 vs 44.1); equal at 16 MiB.
 std::atomic<long> g_opt_host_zero_copy{long(env_size("SWEC_HOST_ZERO_COPY", 2))};
-std::atomic<long> g_opt_host_zero_copy_max{long(env_size("SWEC_HOST_ZERO_COPY_MAX", size_t(4) << 20))};
+std::atomic<long> g_opt_host_zero_copy_max{long(env_size("SWEC_HOST_ZERO_COPY_MAX", size_t(2) << 20))};
 std::atomic<long> g_opt_host_copy_spin_us{long(env_size("SWEC_HOST_COPY_SPIN_US", 200))};
 std::atomic<long> g_opt_host_copy_threads{long(env_size("SWEC_HOST_COPY_THREADS", 0))};  // 0 = auto
 std::atomic<long> g_opt_file_direct_io{long(env_size("SWEC_FILE_DIRECT", 0)) & 3};
@@ -344,12 +346,12 @@ int swec_encoder_impl::apply(const Matrix& rows, const uint8_t* const* in, uint8
         if (is_rs10x4_parity(*this, rows)) {
             fill(p, 0, R, 0);
             SWEC_CUDA(launch_rs10x4_encode(p, layout.blocked, s));
-        } else if (const int aot = (rs10x4 && R <= 4 && K == 10 && g_opt_use_aot.load()) ? aot_recon_find(R, K, rows.v.data()) : -1;
+        } else if (const int aot = (rs10x4 && !layout.blocked && R <= 4 && K == 10 && g_opt_use_aot.load()) ? aot_recon_find(R, K, rows.v.data()) : -1;
                    aot >= 0) {
             // one of the reconstruct matrices compiled with the library (any single-shard loss, shards 0-3 lost):
             // no compile, no threshold — needle-sized degraded reads take the Horner kernel too
             fill(p, 0, R, 0);
-            SWEC_CUDA(launch_aot_recon(aot, p, layout.blocked, s));
+            SWEC_CUDA(launch_aot_recon(aot, p, s));
         } else {
             // specialised (NVRTC) Horner kernel when the stream is long enough to pay for the
             // compile, or the kernel is already cached; otherwise shared-memory tables.
@@ -1268,6 +1270,45 @@ int swec_extract_data_shard_device(swec_encoder* e, const void* dat_v, int64_t d
             have = std::max<int64_t>(0, std::min(have, small));
             if (have) SWEC_CUDA(cudaMemcpyAsync(d3, base + nfull * small_row + int64_t(shard_id) * small, size_t(have), cudaMemcpyDeviceToDevice, s));
             if (have < small) SWEC_CUDA(cudaMemsetAsync(d3 + have, 0, size_t(small - have), s));
+        }
+    }
+    return SWEC_OK;
+}
+
+int swec_write_dat_device(swec_encoder* e, const void* const* data_shards, int64_t dat_size, int64_t large, int64_t small,
+                          void* dat_out, void* stream) {
+    if (!e || !data_shards || !dat_out || dat_size < 0 || large <= 0 || small <= 0)
+        return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    const int k = e->k;
+    for (int i = 0; i < k; i++)
+        if (!data_shards[i]) return fail(SWEC_ERR_INVALID_ARG, "NULL data shard");
+    uint8_t* dat = static_cast<uint8_t*>(dat_out);
+    std::lock_guard<std::mutex> lock(e->mu);
+    int rc = e->ensure_device();
+    if (rc) return rc;
+    cudaStream_t s = pick_stream(e, stream);
+    const int64_t large_row = large * k, small_row = small * k;
+    // WriteDatFile's loops (ec_decoder.go:197-219): `for datFileSize >= dataShards*LargeBlockSize` copies large blocks
+    // round-robin, then small blocks until the size is used up — the last block short
+    const int64_t nlarge = dat_size / large_row;
+    const int64_t rem = dat_size - nlarge * large_row;
+    const int64_t nfull = rem / small_row;
+    const int64_t tail = rem - nfull * small_row;
+    for (int i = 0; i < k; i++) {
+        const uint8_t* sh = static_cast<const uint8_t*>(data_shards[i]);
+        if (nlarge)
+            SWEC_CUDA(cudaMemcpy2DAsync(dat + int64_t(i) * large, size_t(large_row), sh, size_t(large), size_t(large),
+                                        size_t(nlarge), cudaMemcpyDeviceToDevice, s));
+        const uint8_t* sh2 = sh + nlarge * large;
+        uint8_t* base = dat + nlarge * large_row;
+        if (nfull)
+            SWEC_CUDA(cudaMemcpy2DAsync(base + int64_t(i) * small, size_t(small_row), sh2, size_t(small), size_t(small),
+                                        size_t(nfull), cudaMemcpyDeviceToDevice, s));
+        if (tail > 0) {
+            const int64_t have = std::max<int64_t>(0, std::min(tail - int64_t(i) * small, small));
+            if (have)
+                SWEC_CUDA(cudaMemcpyAsync(base + nfull * small_row + int64_t(i) * small, sh2 + nfull * small, size_t(have),
+                                          cudaMemcpyDeviceToDevice, s));
         }
     }
     return SWEC_OK;

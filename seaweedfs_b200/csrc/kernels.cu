@@ -246,13 +246,17 @@ std::atomic<long> g_opt_enc_unroll{env_long("SWEC_ENC_UNROLL", 2)};
 std::atomic<long> g_opt_ctas_per_sm{env_long("SWEC_CTAS_PER_SM", 0)};  // 0 = derive from the shape
 std::atomic<long> g_opt_xt_variant{env_long("SWEC_XT_VARIANT_JIT", SWEC_XT_VARIANT)};
 std::atomic<long> g_opt_use_aot{env_long("SWEC_USE_AOT", 1)};
-std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 1)};
+std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 0)};
 
 // ---- power policy: "heat" = kernel milliseconds recently spent on the device, decaying with a 1 s time
 // constant.  Continuous encoding drives it towards 1000 x duty cycle; a 13-launch burst leaves it below 100.
 // Measured (profiles/r01z_xt_variant_*.jsonl, r01z_batch256_power_modes.txt): the low-power variant wins 4-5 %
 // only when encode launches run back to back for longer than ~0.3 s; with other kernels in between (the
-// 256-volume batch: 38 % duty) the two are equal.  Default is therefore mode 1; auto (0) is opt-in.
+// 256-volume batch: 38 % duty) the two are equal.  Round 2 (profiles/r02b_power_modes.jsonl): the boost variant is the
+// faster one for the first ~0.4 s of back-to-back launches (6.85-7.0 ms per 30 GiB volume, then 7.2-7.4), the low-power
+// one the slower one early (7.4-7.6) and the faster one from then on (6.91-6.95 = 0.998 of the HBM peak); auto switches
+// at 600 ms of kernel time in the last second, i.e. near the crossover, keeps the boost variant for bursts and for the
+// batch (45 % duty), and is therefore the default.
 namespace {
 struct Heat {
     std::mutex mu;

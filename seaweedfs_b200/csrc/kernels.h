@@ -19,9 +19,8 @@ extern std::atomic<long> g_opt_xt_variant, g_opt_use_aot;
 // Power policy (profiles/r01z_xt_variant_probe*.jsonl).  A B200 that encodes back to back for
 // more than a few hundred ms runs into its 1,000 W cap and drops the SM clock to ~1.45 GHz; from then on the
 // 4-instruction multiply-by-2 step (variant 2: fewer instructions, far fewer IMADs) is 4-5 % FASTER than the
-// 5-instruction one that wins while the GPU still boosts.  "power_mode": 1 = always the boost-clock variant
-// (default), 2 = always the low-power variant, 0 = auto (low-power once the Horner kernels own > 60 % of the
-// device's last second).
+// 5-instruction one that wins while the GPU still boosts.  "power_mode": 0 = auto (default: low-power once the Horner kernels
+// own > 60 % of the device's last second), 1 = always the boost-clock variant, 2 = always the low-power variant.
 extern std::atomic<long> g_opt_power_mode;
 void note_kernel_work(double est_ms);   // called by every Horner launch: feeds the auto policy
 bool low_power_now();                   // which variant the next Horner launch on the current device takes
@@ -32,7 +31,7 @@ cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStr
 // aot_recon.cu: reconstruct matrices compiled with the library (every single-shard loss of RS(10,4) + the worst case)
 int aot_recon_find(int r, int k, const unsigned char* coef);  // index or -1
 int aot_recon_count();
-cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, bool blocked, cudaStream_t s);
+cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, cudaStream_t s);  // flat layout
 // replicated_tables: [K][2][16][32] words (lane-replicated), device memory, 16-byte aligned
 cudaError_t launch_table_apply(const SwecApplyParams& p, const u32* replicated_tables, int K, int r, cudaStream_t s);
 // compact_tables: [K][2][16] words, device memory

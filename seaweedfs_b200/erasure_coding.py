@@ -167,6 +167,13 @@ class Encoder:
         check(lib().swec_extract_data_shard_device(self._h, dat_ptr, dat_size, large_block, small_block,
                                                    shard_id, out_ptr, stream))
 
+    def write_dat_device(self, data_shard_ptrs, dat_size: int, dat_out_ptr: int, stream: int = 0,
+                         large_block: int = ErasureCodingLargeBlockSize,
+                         small_block: int = ErasureCodingSmallBlockSize) -> None:
+        """WriteDatFile on device memory (ec_decoder.go:176-223): un-stripe the k data shards into the volume image."""
+        check(lib().swec_write_dat_device(self._h, _ptrs(data_shard_ptrs), dat_size, large_block, small_block,
+                                          dat_out_ptr, stream))
+
     def synchronize(self, stream: int = 0) -> None:
         check(lib().swec_stream_synchronize(self._h, stream))
 

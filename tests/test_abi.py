@@ -149,8 +149,8 @@ def test_set_option_validation(swec):
         assert L.swec_set_option(name, bad) == -1, name
         assert L.swec_set_option(name, good) == 0, name
     assert L.swec_set_option(b"no_such_option", 1) == -1 and L.swec_set_option(None, 1) == -1
-    for name, dflt in ((b"power_mode", 1), (b"xt_variant", 0), (b"use_aot", 1), (b"stage_slots", 3), (b"enc_threads", 512),
-                       (b"host_pieces", 4), (b"host_min_chunk", 128 << 10)):
+    for name, dflt in ((b"power_mode", 0), (b"xt_variant", 0), (b"use_aot", 1), (b"stage_slots", 3), (b"enc_threads", 512),
+                       (b"host_pieces", 4), (b"host_min_chunk", 256 << 10)):
         assert L.swec_set_option(name, dflt) == 0
 
 

@@ -158,7 +158,7 @@ def test_host_seam_every_path_is_bit_exact(cuda, swec, oracle, zero_copy, pieces
         e.close()
         assert L.swec_set_option(b"host_zero_copy", 2) == 0
         assert L.swec_set_option(b"host_pieces", 4) == 0
-        assert L.swec_set_option(b"host_min_chunk", 128 << 10) == 0
+        assert L.swec_set_option(b"host_min_chunk", 256 << 10) == 0
 
 
 @pytest.mark.parametrize("n", [1, 50, 256 * 1024, 5 * 1024 * 1024 + 77])
@@ -770,4 +770,102 @@ def test_power_mode_variants_are_bit_exact(cuda, swec, oracle, mode):
                 assert (allsh[i].cpu().numpy() == data[i]).all(), (mode, k, m, i)
             e.close()
     finally:
-        L.swec_set_option(b"power_mode", 1)
+        L.swec_set_option(b"power_mode", 0)
+
+
+# ---------------------------------------------------------------- round 2: AOT decode kernels, device WriteDatFile
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_aot_reconstruct_kernels_every_matrix_bit_exact(cuda, swec, oracle, mode):
+    """The 15 reconstruct matrices compiled with the library (aot_recon.cu: every single-shard loss of RS(10,4) and
+    shards 0-3 lost), in both multiply-by-2 spellings, against the oracle's Reconstruct — short streams too, since these
+    kernels have no warm-up threshold (a needle-sized degraded read takes them).  No NVRTC compile may happen."""
+    import ctypes as C
+    torch = cuda
+    L = swec.lib()
+    assert L.swec_set_option(b"power_mode", mode) == 0
+    e = swec.erasure_coding.Encoder(10, 4, device=0)
+    try:
+        c0 = C.c_uint64(0)
+        L.swec_jit_stats(C.byref(c0), None, None)
+        for n in (4096 + 48, 3 * (1 << 20) + 16):
+            rng = np.random.default_rng(n + mode)
+            data = [rng.integers(0, 256, n, dtype=np.uint8) for _ in range(10)]
+            full = data + oracle.encode(10, 4, data)
+            d = [dev(torch, x) for x in full]
+            for lost in [(i,) for i in range(14)] + [(0, 1, 2, 3)]:
+                work = [t.clone() for t in d]
+                for i in lost:
+                    work[i].zero_()
+                l0 = L.swec_kernel_launches()
+                e.reconstruct_device([t.data_ptr() for t in work], [0 if i in lost else 1 for i in range(14)], n, False,
+                                     stream(torch))
+                torch.cuda.synchronize()
+                assert L.swec_kernel_launches() - l0 == 1
+                for i in lost:
+                    assert torch.equal(work[i], d[i]), (mode, n, lost, i)
+        c1 = C.c_uint64(0)
+        L.swec_jit_stats(C.byref(c1), None, None)
+        assert c1.value == c0.value, "an AOT pattern went to NVRTC"
+    finally:
+        e.close()
+        L.swec_set_option(b"power_mode", 0)
+
+
+@pytest.mark.parametrize("dat_size,large,small", [
+    (10 * 4096 * 5 + 10 * 512 * 3 + 77, 4096, 512), (10 * 4096 * 2, 4096, 512), (5, 4096, 512), (10 * 512 * 4 + 1, 4096, 512),
+    (3 * 10 * (1 << 20) + 12345, 1 << 30, 1 << 20), (2 * 10 * (1 << 22) + 7 * 10 * (1 << 20) + 999_999, 1 << 22, 1 << 20)])
+def test_write_dat_device_is_the_inverse_of_the_striping(cuda, swec, oracle, dat_size, large, small):
+    """WriteDatFile on the GPU (ec_decoder.go:176-223): the k data shards in HBM -> the .dat image, equal to the oracle's
+    WriteDatFile and to the original volume; combined with reconstruct_device it is ec.decode of a volume that lost
+    data shards without leaving the device."""
+    torch = cuda
+    ec = swec.erasure_coding
+    e = ec.Encoder(10, 4, device=0)
+    try:
+        dat = oracle.synth(0, dat_size, SEED ^ dat_size)
+        shards = oracle.encode_dat_image(dat, large=large, small=small)
+        assert (oracle.write_dat_image(shards, dat_size, large=large, small=small) == dat).all()
+        dsh = [dev(torch, s_) for s_ in shards]
+        out = torch.full((dat_size + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+        e.write_dat_device([t.data_ptr() for t in dsh[:10]], dat_size, out.data_ptr(), stream(torch), large, small)
+        torch.cuda.synchronize()
+        assert (out[:dat_size].cpu().numpy() == dat).all()
+        assert int((out[dat_size:] != 0xEE).sum()) == 0, "wrote past the end of the image"
+        # lose data shards 2 and 7, rebuild them in HBM, assemble again
+        n = len(shards[0])
+        if n % 16 == 0 or True:
+            work = [t.clone() for t in dsh]
+            work[2].zero_()
+            work[7].zero_()
+            e.reconstruct_device([t.data_ptr() for t in work], [0 if i in (2, 7) else 1 for i in range(14)], n, True, stream(torch))
+            out.fill_(0)
+            e.write_dat_device([t.data_ptr() for t in work[:10]], dat_size, out.data_ptr(), stream(torch), large, small)
+            torch.cuda.synchronize()
+            assert (out[:dat_size].cpu().numpy() == dat).all()
+    finally:
+        e.close()
+
+
+def test_failed_rebuild_leaves_no_output_and_reports_no_ids(cuda, swec, oracle, tmp_path):
+    """generateMissingEcFiles returns nil ids with an error (ec_encoder.go:146-200); a half-written shard must not stay
+    behind either, because findShardFile would take it for a present input next time."""
+    import ctypes as C
+    ec = swec.erasure_coding
+    dat = oracle.synth(0, 3_000_000, SEED + 9)
+    base = str(tmp_path / "3")
+    dat.tofile(base + ".dat")
+    ec.write_ec_files(base)
+    os.remove(base + ".ec03")
+    os.remove(base + ".ec11")
+    with open(base + ".ec05", "ab") as f:          # one present shard longer than the others: size mismatch
+        f.write(b"x" * 4096)
+    ids = (C.c_uint32 * 32)(*([7] * 32))
+    n = C.c_int(5)
+    rc = swec.lib().swec_rebuild_ec_files(base.encode(), None, 0, 10, 4, 0, ids, C.byref(n))
+    assert rc == -6 and n.value == 0               # SWEC_ERR_SHARD_SIZE, no ids
+    assert not os.path.exists(base + ".ec03") and not os.path.exists(base + ".ec11")
+    # and the shard files of a successful generate have exactly the expected size while being written with reserved extents
+    want = ec.expected_shard_size(len(dat))
+    for i in (0, 9, 13):
+        assert os.path.getsize(base + ec.ToExt(i)) == (want if i != 5 else want + 4096)
