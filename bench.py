@@ -506,6 +506,17 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path")
+    # Placement: rank r drives the r-th GPU of the library's socket-interleaved order (0,4,1,5,… on this pool's boxes)
+    # when the box shows more GPUs than ranks — N = 2 and 4 then use both sockets' memory controllers for the host-fed
+    # e2e leg instead of crowding socket 0 (SCALE_r01: 4 GPUs of one socket share ~142 GB/s of H2D).
+    rank_local = local
+    placement = "cuda:%d (LOCAL_RANK)" % local
+    if torch.cuda.device_count() > world and not os.environ.get("SWEC_BENCH_NO_SPREAD"):
+        order = (C.c_int * 64)()
+        cnt = C.c_int(0)
+        if seaweedfs_b200.lib().swec_device_spread_order(order, 64, C.byref(cnt)) == 0 and cnt.value > local:
+            local = int(order[local])
+            placement = "cuda:%d = entry %d of swec_device_spread_order %s" % (local, rank_local, list(order[:cnt.value]))
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -796,7 +807,7 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"RS(10,4) encode of one {args.volume_gib:g} GiB synthetic volume per GPU "
                                    "(BASELINE configs[1]); 10x1 GiB large-block rows, HBM-resident",
-                       "dat_bytes_per_gpu": dat_size, "shard_bytes": shard, "volumes": world,
+                       "dat_bytes_per_gpu": dat_size, "shard_bytes": shard, "volumes": world, "rank0_device": placement,
                        "l2": "inputs (30 GiB) far exceed the 126 MB L2; no flush needed",
                        "wake_up": "20 digest passes over the volume (~120 ms) before the legs: the GPU leaves idle clocks",
                        "seed": hex(SEED0), "check": checked},

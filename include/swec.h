@@ -75,6 +75,10 @@ int swec_device_count(int *count);            /* SWEC_ERR_NO_DEVICE when the dri
  * process down in stages (CPython's Py_Finalize) call this from their own exit hook; the library
  * also registers it with atexit().  Everything keeps working afterwards, without background JIT. */
 void swec_shutdown(void);
+/* Device ids interleaved over the host's NUMA nodes (0,4,1,5,… on a 2-socket, 8-GPU box): the first n entries are the
+ * n GPUs a process should use for n concurrent host-fed volumes — one socket cannot feed four GPUs at full PCIe rate.
+ * This is the order swecPickDevice walks; weed/shell/command_ec_encode.go:302-315 runs the volumes.   */
+int swec_device_spread_order(int *order, int capacity, int *count);
 uint64_t swec_kernel_launches(void);          /* kernels this process has launched (all devices) */
 /* Tuning: "enc_threads" {128,256,512}, "enc_unroll" {1,2}, "ctas_per_sm" (0 = auto),
  * "stage_chunk" (bytes per shard per staging slot), "stage_slots", "host_pieces" (a host-buffer call is cut into at

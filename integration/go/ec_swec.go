@@ -25,16 +25,19 @@ import (
 
 // One volume server process drives every GPU of the box: each encoder / file-level call takes the next
 // GPU round-robin (volume v → GPU v mod N — independent volumes need no collective), the same way the
-// shell already runs up to 10 volumes concurrently (weed/shell/common.go:11).  Set -ec.gpu=N to pin one.
+// shell already runs up to 10 volumes concurrently (weed/shell/common.go:11).  The round-robin walks the
+// library's socket-interleaved order (0,4,1,5,… on a two-socket box): n concurrent volumes then use both
+// sockets' memory controllers — one socket cannot feed four GPUs at full PCIe rate.  Set -ec.gpu=N to pin one.
 var (
-	swecPinned   = -1 // -ec.gpu flag; -1 = round-robin over all devices
-	swecNext     uint32
-	swecGPUCount = func() int {
+	swecPinned  = -1 // -ec.gpu flag; -1 = round-robin over all devices
+	swecNext    uint32
+	swecDevices = func() []C.int {
+		var order [64]C.int
 		var n C.int
-		if C.swec_device_count(&n) != C.SWEC_OK || n < 1 {
-			return 1 // calls will fail with SWEC_ERR_NO_DEVICE and surface as Go errors
+		if C.swec_device_spread_order(&order[0], 64, &n) != C.SWEC_OK || n < 1 {
+			return []C.int{0} // calls will fail with SWEC_ERR_NO_DEVICE and surface as Go errors
 		}
-		return int(n)
+		return append([]C.int(nil), order[:int(n)]...)
 	}()
 )
 
@@ -42,7 +45,7 @@ func swecPickDevice() C.int {
 	if swecPinned >= 0 {
 		return C.int(swecPinned)
 	}
-	return C.int(int(atomic.AddUint32(&swecNext, 1)) % swecGPUCount)
+	return swecDevices[int(atomic.AddUint32(&swecNext, 1))%len(swecDevices)]
 }
 
 type swecEncoder struct {

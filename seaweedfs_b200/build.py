@@ -23,7 +23,7 @@ LIB = os.path.join(HERE, "libswec.so")
 ROOT = os.path.dirname(HERE)
 
 SOURCES = ["kernels.cu", "aot_recon.cu", "engine.cc", "ec_files.cc", "ec_index.cc", "ec_volume.cc", "jit.cc", "codegen.cc", "gf256.cc"]
-HEADERS = ["apply_params.h", "device_common.cuh", "kernels.h", "engine.h", "gf256.h", "codegen.h", "io_pool.h",
+HEADERS = ["apply_params.h", "device_common.cuh", "kernels.h", "engine.h", "gf256.h", "codegen.h", "io_pool.h", "mini_json.h",
            os.path.join(ROOT, "include", "swec.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static"]

@@ -30,6 +30,7 @@
 
 #include "engine.h"
 #include "io_pool.h"
+#include "mini_json.h"
 
 namespace swec {
 namespace {
@@ -465,22 +466,13 @@ bool read_vif_ratio(const std::string& path, int* ds, int* ps) {
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) txt.append(buf, n);
     fclose(f);
-    const size_t cfg = txt.find("\"ecShardConfig\"");
-    if (cfg == std::string::npos) return false;
-    auto number_after = [&](const char* key, int* out) {
-        const size_t p = txt.find(key, cfg);
-        if (p == std::string::npos) return false;
-        size_t q = txt.find(':', p);
-        if (q == std::string::npos) return false;
-        q++;
-        while (q < txt.size() && (txt[q] == ' ' || txt[q] == '"' || txt[q] == '\t' || txt[q] == '\n')) q++;
-        *out = atoi(txt.c_str() + q);
-        return true;
-    };
-    int a = 0, b = 0;
-    if (!number_after("\"dataShards\"", &a) || !number_after("\"parityShards\"", &b)) return false;
-    *ds = a;
-    *ps = b;
+    int64_t a = 0, b = 0;
+    if (!mini_json::nested_int(txt, "ecShardConfig", "ec_shard_config", "dataShards", "data_shards", &a) ||
+        !mini_json::nested_int(txt, "ecShardConfig", "ec_shard_config", "parityShards", "parity_shards", &b))
+        return false;
+    if (a < 0 || b < 0 || a > 255 || b > 255) return false;
+    *ds = int(a);
+    *ps = int(b);
     return true;
 }
 

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "mini_json.h"
 
 namespace swec {
 
@@ -102,16 +103,9 @@ void ratio_from_vif(const std::string& data_base, int* k, int* m) {
 
 // A numeric field of a protobuf-JSON .vif (64-bit integers are rendered as strings); false when absent.
 bool vif_number(const std::string& txt, const char* key, int64_t* out) {
-    const std::string k = std::string("\"") + key + "\"";
-    const size_t p = txt.find(k);
-    if (p == std::string::npos) return false;
-    size_t q = txt.find(':', p + k.size());
-    if (q == std::string::npos) return false;
-    q++;
-    while (q < txt.size() && (txt[q] == ' ' || txt[q] == '"' || txt[q] == '\t' || txt[q] == '\n')) q++;
-    if (q >= txt.size() || !(isdigit((unsigned char)txt[q]) || txt[q] == '-')) return false;
-    *out = strtoll(txt.c_str() + q, nullptr, 10);
-    return true;
+    const std::string k(key);
+    const char* alt = k == "datFileSize" ? "dat_file_size" : k == "expireAtSec" ? "expire_at_sec" : nullptr;
+    return mini_json::top_int(txt, key, alt, out);
 }
 
 bool slurp(const std::string& path, std::string* out) {

@@ -802,6 +802,31 @@ int swec_device_count(int* count) {
     return n > 0 ? SWEC_OK : fail(SWEC_ERR_NO_DEVICE, "no CUDA devices");
 }
 
+// Placement order for a process (or a launcher) that drives several GPUs: device ids interleaved over the host's
+// NUMA nodes — 0,4,1,5,2,6,3,7 on a box with GPUs 0-3 on socket 0 and 4-7 on socket 1.  Host-fed work is bound by
+// what ONE socket can DMA (4 GPUs behind one socket: ~142 GB/s in, SCALE_r01.json), so the first n devices of this
+// order spread n concurrent volumes over both sockets' memory controllers and root complexes instead of filling
+// socket 0 first.  Devices whose node is unknown keep their index order at the end.
+int swec_device_spread_order(int* order, int capacity, int* count) {
+    if (!order || !count || capacity <= 0) return fail(SWEC_ERR_INVALID_ARG, "bad argument");
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(SWEC_ERR_NO_DEVICE, "no CUDA devices");
+    }
+    std::map<int, std::vector<int>> by_node;  // node → devices, both ascending
+    for (int d = 0; d < n; d++) by_node[getenv("SWEC_NO_NUMA") ? -1 : device_numa_node(d)].push_back(d);
+    std::vector<int> out;
+    for (size_t round = 0; out.size() < size_t(n); round++)
+        for (auto& kv : by_node)
+            if (round < kv.second.size()) out.push_back(kv.second[round]);
+    *count = std::min(n, capacity);
+    for (int i = 0; i < *count; i++) order[i] = out[size_t(i)];
+    return SWEC_OK;
+}
+
 uint64_t swec_kernel_launches(void) { return g_kernel_launches.load(); }
 
 void swec_shutdown(void) {

@@ -237,6 +237,15 @@ def test_jit_source_compiles_for_sm100a_without_gpu(swec):
         print(rows.shape, size.value, steps.value, xors.value, round(time.perf_counter() - t0, 3))
 
 
+def test_device_spread_order_without_devices(swec):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    order, cnt = (C.c_int * 8)(), C.c_int(-1)
+    assert swec.lib().swec_device_spread_order(order, 8, C.byref(cnt)) == -7 and cnt.value == 0     # SWEC_ERR_NO_DEVICE
+    assert swec.lib().swec_device_spread_order(None, 8, C.byref(cnt)) == -1
+
+
 def test_cubin_disk_cache_and_aot_table(swec, tmp_path, monkeypatch):
     """The decode-kernel cache outlives the process: a matrix compiled once is loaded from the on-disk cubin cache
     the next time (no NVRTC compile), and the 15 most common reconstruct matrices are compiled with the library."""

@@ -220,3 +220,28 @@ def test_file_pipeline_write_error_surfaces_and_does_not_hang(cuda, swec, tmp_pa
     r = subprocess.run([sys.executable, "-c", child], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert "ERR SWEC_ERR_IO" in r.stdout and "pwrite" in r.stdout, r.stdout[-2000:]
     assert "RETRY OK 6291456" in r.stdout, r.stdout[-2000:]
+
+
+def test_device_spread_order_is_a_permutation_interleaved_over_numa_nodes(cuda, swec):
+    """swec_device_spread_order: every device exactly once; consecutive entries alternate between the host's NUMA
+    nodes for as long as both have devices left (what bench.py and swecPickDevice use to place n concurrent volumes)."""
+    import ctypes as C
+    torch = cuda
+    n = torch.cuda.device_count()
+    order, cnt = (C.c_int * 64)(), C.c_int(0)
+    assert swec.lib().swec_device_spread_order(order, 64, C.byref(cnt)) == 0
+    got = list(order[:cnt.value])
+    assert sorted(got) == list(range(n))
+    if n >= 2:
+        import pynvml
+        pynvml.nvmlInit()
+        nodes = []
+        for d in got:
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(d)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            try:
+                nodes.append(int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read()))
+            except OSError:
+                nodes.append(-1)
+        if len(set(nodes)) == 2 and nodes.count(nodes[0]) == n // 2:
+            assert all(nodes[i] != nodes[i + 1] for i in range(n - 1)), (got, nodes)

@@ -270,3 +270,30 @@ def test_ec_volume_ratio_from_vif(swec, tmp_path, vif, want):
     assert info["version"] == (2 if vif is not None else 3) and info["local_shards"] == [0]
     assert info["shard_dat_size"] == (123456 // want[0] if vif is not None else 8 - 1)
     ev.close()
+
+
+@pytest.mark.parametrize("text,want", [
+    # member order reversed, a decoy key inside a string value, escapes, nested arrays before the real object
+    ('{"bytesOffset": 7, "note": "\\"ecShardConfig\\": {\\"dataShards\\": 3}", "files": [{"dataShards": 5}], '
+     '"ecShardConfig": {"parityShards": "2", "dataShards": 7}, "datFileSize": "99", "version": 3}', (7, 2, 99, 3)),
+    # proto field names (protojson accepts both spellings), numbers unquoted, odd whitespace
+    ('{\n"version"\t:\t2 ,"dat_file_size":1234,"ec_shard_config":{ "data_shards" : 4 ,\n "parity_shards":1}}', (4, 1, 1234, 2)),
+    # dataShards appears only OUTSIDE ecShardConfig: the ratio must fall back to 10+4
+    ('{"dataShards": 6, "parityShards": 3, "version": 3, "datFileSize": "50"}', (10, 4, 50, 3)),
+    # malformed JSON: nothing is taken from it
+    ('{"version": 2, "ecShardConfig": {"dataShards": 6, "parityShards": 3', (10, 4, None, 3)),
+])
+def test_vif_is_parsed_as_json_not_by_substring(swec, tmp_path, text, want):
+    """.vif is protobuf-JSON (weed/storage/volume_info/volume_info.go:73-95): member order, escapes and look-alike keys
+    inside strings or other objects must not matter (csrc/mini_json.h)."""
+    ec = swec.erasure_coding
+    base = str(tmp_path / "v_1")
+    open(base + ".ecx", "wb").write(b"")
+    open(base + ".ec00", "wb").write(bytes(8))
+    open(base + ".vif", "w").write(text)
+    ev = ec.EcVolume(base, device=-1)
+    info = ev.info()
+    ds, ps, dat, ver = want
+    assert (info["data_shards"], info["parity_shards"], info["version"]) == (ds, ps, ver)
+    assert info["shard_dat_size"] == (dat // ds if dat is not None else 8 - 1)
+    ev.close()
