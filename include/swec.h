@@ -100,8 +100,10 @@ int swec_debug_jit_compile(int r, int k, const uint8_t *rows, size_t *cubin_byte
  * `aot_matrices` reconstruct matrices compiled with the library (every single-shard loss of RS(10,4) and shards 0-3
  * lost: no compile, no NVRTC, any stream length); an on-disk cubin cache shared by every process
  * ($SWEC_CACHE_DIR, else $XDG_CACHE_HOME/swec, else ~/.cache/swec; SWEC_NO_DISK_CACHE=1 disables) whose hits are
- * counted in `disk_cache_hits`; NVRTC for patterns never seen before (`nvrtc_compiles`).  Any pointer may be NULL. */
-int swec_jit_stats(uint64_t *nvrtc_compiles, uint64_t *disk_cache_hits, int *aot_matrices);
+ * counted in `disk_cache_hits`; NVRTC for patterns never seen before (`nvrtc_compiles`).  `aot_launches` = launches of
+ * the compiled-in reconstruct kernels by this process.  Any pointer may be NULL. */
+int swec_jit_stats(uint64_t *nvrtc_compiles, uint64_t *disk_cache_hits, int *aot_matrices,
+                   uint64_t *aot_launches);
 
 /* ---- encoder = reedsolomon.New(dataShards, parityShards) ----------------------------------- */
 /* device < 0: host-side object only (matrix queries); compute calls then fail with NO_DEVICE.  */

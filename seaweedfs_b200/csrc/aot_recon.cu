@@ -10,6 +10,7 @@
 // (codegen_main.cc --aot-recon 10 4); both multiply-by-2 spellings are compiled, like the encode kernel.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstring>
 
 #ifndef SWEC_XT_VARIANT
@@ -53,6 +54,9 @@ int aot_recon_find(int r, int k, const unsigned char* coef) {
 
 int aot_recon_count() { return SWEC_AOT_RECON_COUNT; }
 
+static std::atomic<unsigned long long> g_aot_launches{0};
+unsigned long long aot_recon_launches() { return g_aot_launches.load(); }
+
 cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, cudaStream_t s) {
     if (p.nvec == 0) return cudaSuccess;
     if (idx < 0 || idx >= SWEC_AOT_RECON_COUNT) return cudaErrorInvalidValue;
@@ -67,6 +71,7 @@ cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, cudaStream_t s) 
     const bool lp = low_power_now();
     note_kernel_work(double(p.nvec) * 16.0 * double(kAotReconKeys[idx].k + kAotReconKeys[idx].r) / 6.2e9 * 1e3);
     g_kernel_launches++;
+    g_aot_launches++;
     switch (idx) {
 #define SWEC_AOT_CASE(I)                                                                              \
     case I:                                                                                           \

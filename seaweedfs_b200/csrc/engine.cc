@@ -834,7 +834,8 @@ void swec_shutdown(void) {
     file_pipeline_trim();
 }
 
-int swec_jit_stats(uint64_t* nvrtc_compiles, uint64_t* disk_cache_hits, int* aot_matrices) {
+int swec_jit_stats(uint64_t* nvrtc_compiles, uint64_t* disk_cache_hits, int* aot_matrices, uint64_t* aot_launches) {
+    if (aot_launches) *aot_launches = aot_recon_launches();
     if (nvrtc_compiles) *nvrtc_compiles = jit_compile_count();
     if (disk_cache_hits) *disk_cache_hits = jit_disk_hit_count();
     if (aot_matrices) *aot_matrices = aot_recon_count();

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 
 #ifndef SWEC_XT_VARIANT
@@ -292,7 +293,10 @@ bool low_power_now() {
     Heat& h = heat_here();
     const auto now = std::chrono::steady_clock::now();
     std::lock_guard<std::mutex> lk(h.mu);
-    return decayed(h, now) > kHeatHotMs;
+    const double level = decayed(h, now);
+    static const bool debug = getenv("SWEC_DEBUG_POWER") != nullptr;
+    if (debug) fprintf(stderr, "[swec] power policy: heat %.1f ms (hot above %.0f) -> %s variant\n", level, kHeatHotMs, level > kHeatHotMs ? "low-power" : "boost");
+    return level > kHeatHotMs;
 }
 
 int effective_xt_variant() {

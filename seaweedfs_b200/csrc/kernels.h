@@ -31,6 +31,7 @@ cudaError_t launch_rs10x4_encode(const SwecApplyParams& p, bool blocked, cudaStr
 // aot_recon.cu: reconstruct matrices compiled with the library (every single-shard loss of RS(10,4) + the worst case)
 int aot_recon_find(int r, int k, const unsigned char* coef);  // index or -1
 int aot_recon_count();
+unsigned long long aot_recon_launches();  // launches of those kernels by this process
 cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, cudaStream_t s);  // flat layout
 // replicated_tables: [K][2][16][32] words (lane-replicated), device memory, 16-byte aligned
 cudaError_t launch_table_apply(const SwecApplyParams& p, const u32* replicated_tables, int K, int r, cudaStream_t s);

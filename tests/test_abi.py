@@ -253,19 +253,19 @@ def test_cubin_disk_cache_and_aot_table(swec, tmp_path, monkeypatch):
     from oracle import rs_numpy as rn
     L = swec.lib()
     aot = C.c_int(0)
-    assert L.swec_jit_stats(None, None, C.byref(aot)) == 0 and aot.value == 15       # 14 single losses + shards 0-3
+    assert L.swec_jit_stats(None, None, C.byref(aot), None) == 0 and aot.value == 15       # 14 single losses + shards 0-3
     monkeypatch.setenv("SWEC_CACHE_DIR", str(tmp_path / "cubins"))
     rows = np.ascontiguousarray(rn.fused_reconstruct_rows(10, 4, [i not in (3, 7, 12) for i in range(14)])[2], dtype=np.uint8)
 
     def compile_once():
         c0, h0 = C.c_uint64(0), C.c_uint64(0)
-        L.swec_jit_stats(C.byref(c0), C.byref(h0), None)
+        L.swec_jit_stats(C.byref(c0), C.byref(h0), None, None)
         size = C.c_size_t(0)
         t0 = time.perf_counter()
         rc = L.swec_debug_jit_compile(rows.shape[0], rows.shape[1], rows.ctypes.data, C.byref(size), None, None)
         dt = time.perf_counter() - t0
         c1, h1 = C.c_uint64(0), C.c_uint64(0)
-        L.swec_jit_stats(C.byref(c1), C.byref(h1), None)
+        L.swec_jit_stats(C.byref(c1), C.byref(h1), None, None)
         return rc, size.value, c1.value - c0.value, h1.value - h0.value, dt
 
     rc, size, compiles, hits, _ = compile_once()

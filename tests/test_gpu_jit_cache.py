@@ -35,7 +35,7 @@ for name, lost in (("single_data", (6,)), ("single_parity", (12,)), ("worst", (0
     for i in lost:
         work[i].zero_()
     c0, h0 = C.c_uint64(0), C.c_uint64(0)
-    L.swec_jit_stats(C.byref(c0), C.byref(h0), None)
+    L.swec_jit_stats(C.byref(c0), C.byref(h0), None, None)
     l0 = L.swec_kernel_launches()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -44,7 +44,7 @@ for name, lost in (("single_data", (6,)), ("single_parity", (12,)), ("worst", (0
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     c1, h1 = C.c_uint64(0), C.c_uint64(0)
-    L.swec_jit_stats(C.byref(c1), C.byref(h1), None)
+    L.swec_jit_stats(C.byref(c1), C.byref(h1), None, None)
     ok = all(torch.equal(work[i], dev[i]) for i in lost)
     out[name] = {"ok": ok, "compiles": c1.value - c0.value, "disk_hits": h1.value - h0.value,
                  "first_call_ms": round(dt * 1e3, 2), "launches": L.swec_kernel_launches() - l0}
