@@ -96,6 +96,10 @@ int swec_set_option(const char *name, long value);
  * loading it — needs no GPU.  Reports the cubin size and the generator's instruction statistics.  */
 int swec_debug_jit_compile(int r, int k, const uint8_t *rows, size_t *cubin_bytes, int *xtime_steps,
                            int *xor_ops);
+/* Diagnostics of "power_mode" auto: `heat_ms` = estimated Horner-kernel milliseconds the device ran during the last
+ * second (exponentially decayed; continuous encoding tends to 1000), `low_power` = the variant the next launch takes
+ * (1 once heat_ms exceeds 450).  device < 0: the calling thread's current device.                                  */
+int swec_debug_power_state(int device, double *heat_ms, int *low_power);
 /* The decode-kernel cache (GPU analogue of the decode-matrix LRU, rse/src/core.rs:25,700-734), three tiers:
  * `aot_matrices` reconstruct matrices compiled with the library (every single-shard loss of RS(10,4) and shards 0-3
  * lost: no compile, no NVRTC, any stream length); an on-disk cubin cache shared by every process

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "swec_kernel_launches": (C.c_uint64, []),
     "swec_set_option": (C.c_int, [C.c_char_p, C.c_long]),
     "swec_device_spread_order": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "swec_debug_power_state": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "swec_jit_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "swec_debug_jit_compile": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int)]),

@@ -69,7 +69,7 @@ cudaError_t launch_aot_recon(int idx, const SwecApplyParams& p, cudaStream_t s) 
     const u64 cap = u64(sms) * (kAotReconKeys[idx].r >= 3 ? 1 : 2);
     const unsigned grid = unsigned(need < cap ? need : cap);
     const bool lp = low_power_now();
-    note_kernel_work(double(p.nvec) * 16.0 * double(kAotReconKeys[idx].k + kAotReconKeys[idx].r) / 6.2e9 * 1e3);
+    note_kernel_work(double(p.nvec) * 16.0 * double(kAotReconKeys[idx].k + kAotReconKeys[idx].r) / 6.2e12 * 1e3);
     g_kernel_launches++;
     g_aot_launches++;
     switch (idx) {

@@ -842,6 +842,13 @@ int swec_jit_stats(uint64_t* nvrtc_compiles, uint64_t* disk_cache_hits, int* aot
     return SWEC_OK;
 }
 
+int swec_debug_power_state(int device, double* heat_ms, int* low_power) {
+    if (device >= 0) SWEC_CUDA(cudaSetDevice(device));
+    if (heat_ms) *heat_ms = power_heat_ms();
+    if (low_power) *low_power = low_power_now() ? 1 : 0;
+    return SWEC_OK;
+}
+
 int swec_debug_jit_compile(int r, int k, const uint8_t* rows, size_t* cubin_bytes, int* xtime_steps, int* xor_ops) {
     if (r <= 0 || k <= 0 || k > SWEC_MAX_INPUTS || !rows) return fail(SWEC_ERR_INVALID_ARG, "bad matrix");
     Matrix m(r, k);

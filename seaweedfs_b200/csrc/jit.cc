@@ -390,7 +390,7 @@ cudaError_t jit_launch(const JitKernel& k, const SwecApplyParams& p, bool blocke
     const u64 cap = u64(sms) * u64(encode_ctas_per_sm());
     const unsigned grid = unsigned(need < cap ? need : cap);
     void* args[] = {const_cast<SwecApplyParams*>(&p)};
-    note_kernel_work(double(p.nvec) * 16.0 * 14.0 / 6.2e9 * 1e3);  // ≈ k + r streams; feeds the power policy
+    note_kernel_work(double(p.nvec) * 16.0 * 14.0 / 6.2e12 * 1e3);  // ≈ k + r streams; feeds the power policy
     g_kernel_launches++;
     return cudaLaunchKernel(reinterpret_cast<const void*>(blocked ? k.blocked : k.flat), dim3(grid),
                             dim3(unsigned(k.threads)), args, 0, s);

@@ -256,7 +256,7 @@ std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 0)};
 // 256-volume batch: 38 % duty) the two are equal.  Round 2 (profiles/r02b_power_modes.jsonl): the boost variant is the
 // faster one for the first ~0.4 s of back-to-back launches (6.85-7.0 ms per 30 GiB volume, then 7.2-7.4), the low-power
 // one the slower one early (7.4-7.6) and the faster one from then on (6.91-6.95 = 0.998 of the HBM peak); auto switches
-// at 600 ms of kernel time in the last second, i.e. near the crossover, keeps the boost variant for bursts and for the
+// at 450 ms of kernel time in the last second, i.e. near the crossover, keeps the boost variant for bursts and for the
 // batch (45 % duty), and is therefore the default.
 namespace {
 struct Heat {
@@ -265,7 +265,9 @@ struct Heat {
     std::chrono::steady_clock::time_point last{};
 };
 Heat g_heat[64];
-constexpr double kHeatTauMs = 1000.0, kHeatHotMs = 600.0;  // hot = the Horner kernels own > 60 % of the last second
+constexpr double kHeatTauMs = 1000.0, kHeatHotMs = 450.0;  // hot = the Horner kernels own > 45 % of the last second:
+// from cold that is ~0.6 s of back-to-back launches, where the measured timelines of the two variants cross (~0.45 s,
+// profiles/r02b_power_modes.jsonl); the 256-volume batch (46 % duty) sits at the threshold, where the variants are equal
 Heat& heat_here() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -299,6 +301,13 @@ bool low_power_now() {
     return level > kHeatHotMs;
 }
 
+double power_heat_ms() {  // diagnostics: the policy's current input on the current device
+    Heat& h = heat_here();
+    const auto now = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lk(h.mu);
+    return decayed(h, now);
+}
+
 int effective_xt_variant() {
     const long v = g_opt_xt_variant.load();
     if (v != 0) return int(v);          // explicit measurement override
@@ -306,7 +315,7 @@ int effective_xt_variant() {
 }
 
 static double est_ms_for(const SwecApplyParams& p, int k, int r) {
-    return double(p.nvec) * 16.0 * double(k + r) / 6.2e9 * 1e3;   // algorithmic bytes at ~6.2 TB/s
+    return double(p.nvec) * 16.0 * double(k + r) / 6.2e12 * 1e3;   // algorithmic bytes at ~6.2 TB/s
 }
 
 int encode_ctas_per_sm() {

@@ -20,9 +20,10 @@ extern std::atomic<long> g_opt_xt_variant, g_opt_use_aot;
 // more than a few hundred ms runs into its 1,000 W cap and drops the SM clock to ~1.45 GHz; from then on the
 // 4-instruction multiply-by-2 step (variant 2: fewer instructions, far fewer IMADs) is 4-5 % FASTER than the
 // 5-instruction one that wins while the GPU still boosts.  "power_mode": 0 = auto (default: low-power once the Horner kernels
-// own > 60 % of the device's last second), 1 = always the boost-clock variant, 2 = always the low-power variant.
+// own > 45 % of the device's last second), 1 = always the boost-clock variant, 2 = always the low-power variant.
 extern std::atomic<long> g_opt_power_mode;
 void note_kernel_work(double est_ms);   // called by every Horner launch: feeds the auto policy
+double power_heat_ms();                 // Horner-kernel milliseconds of the last ~second on the current device (decayed)
 bool low_power_now();                   // which variant the next Horner launch on the current device takes
 int effective_xt_variant();             // variant for run-time specialised kernels (explicit xt_variant wins)
 int encode_ctas_per_sm();

@@ -869,3 +869,48 @@ def test_failed_rebuild_leaves_no_output_and_reports_no_ids(cuda, swec, oracle, 
     want = ec.expected_shard_size(len(dat))
     for i in (0, 9, 13):
         assert os.path.getsize(base + ec.ToExt(i)) == (want if i != 5 else want + 4096)
+
+
+def test_power_policy_auto_keeps_the_boost_variant_for_bursts(cuda, swec):
+    """"power_mode" auto (kernels.cu): the policy's input is the estimated Horner-kernel time of the last second.  One
+    launch over 14 GiB of algorithmic bytes is ~2.4 ms of it, a burst of 13 such launches ~30 ms — far below the 450 ms
+    threshold, so bursts run the boost-clock variant; only ~1 s of back-to-back encoding flips the policy, and two idle
+    seconds flip it back.  (Round-2 regression: the estimate was 1000x too large and every launch after the first
+    took the low-power variant.)"""
+    import ctypes as C
+    import time
+    torch = cuda
+    L = swec.lib()
+    assert L.swec_set_option(b"power_mode", 0) == 0
+    e = swec.erasure_coding.Encoder(10, 4, device=0)
+    n = 1 << 30
+    d = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(14)]
+    ptrs = [t.data_ptr() for t in d]
+    s = stream(torch)
+
+    def state():
+        heat, lp = C.c_double(0), C.c_int(0)
+        assert L.swec_debug_power_state(0, C.byref(heat), C.byref(lp)) == 0
+        return heat.value, lp.value
+    time.sleep(2.5)                                   # whatever earlier tests left behind has decayed
+    h0, lp0 = state()
+    assert h0 < 150 and lp0 == 0, (h0, lp0)
+    e.encode_device(ptrs[:10], ptrs[10:], n, s)
+    h1, lp1 = state()
+    assert 1.0 < h1 - h0 * 0.99 < 6.0 and lp1 == 0, (h0, h1)
+    for _ in range(12):
+        e.encode_device(ptrs[:10], ptrs[10:], n, s)
+    torch.cuda.synchronize()
+    h2, lp2 = state()
+    assert h2 < 200 and lp2 == 0, (h2, lp2)              # a 13-launch burst stays on the boost variant
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 2.0:                # ~2 s of back-to-back encoding
+        for _ in range(20):
+            e.encode_device(ptrs[:10], ptrs[10:], n, s)
+        torch.cuda.synchronize()
+    h3, lp3 = state()
+    assert h3 > 450 and lp3 == 1, (h3, lp3)
+    time.sleep(2.5)
+    h4, lp4 = state()
+    assert h4 < 150 and lp4 == 0, (h4, lp4)
+    e.close()
