@@ -361,6 +361,13 @@ def host_api_leg(L, enc, local, sizes=(256 * 1024, 1 << 20, 16 << 20), min_s=0.4
     return out
 
 
+def power_state(L, device):
+    """(heat_ms, low_power) of the library's auto power policy on `device` (swec_debug_power_state)."""
+    heat, lp = C.c_double(0), C.c_int(0)
+    L.swec_debug_power_state(device, C.byref(heat), C.byref(lp))
+    return heat.value, lp.value
+
+
 def load_batch_golden(n_volumes, dat_size):
     """CPU-oracle digest of the first n volumes of the configs[3] batch (tests/golden/batch256.json, written by
     tests/golden/make_batch_golden.py: every volume regenerated, striped and encoded on the CPU)."""
@@ -393,6 +400,7 @@ def batch_leg(n_volumes, L, enc, dat, dat_size, par, shard, stream, local, rank,
 
     def encode_volume(v, seed):
         assert L.swec_synth_fill_device(local, dat.data_ptr(), 0, dat.numel(), seed, stream) == 0
+        last["lp"] = last.get("lp", 0) + power_state(L, local)[1]
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         enc.encode_volume_device(dat.data_ptr(), dat_size, par_ptrs, stream)
@@ -437,6 +445,7 @@ def batch_leg(n_volumes, L, enc, dat, dat_size, par, shard, stream, local, rank,
             "volumes_per_gpu": encode_launches, "ms_per_volume": round(per_volume_ms, 4),
             "per_rank_ms": [round(x, 3) for x in res["per_rank_ms"]],
             "roofline_frac": round(achieved / peak, 4), "digest": digest, "check": check,
+            "rank0_launches_on_low_power_variant": last.get("lp", 0),
             "sm_mhz": c["sm_mhz"], "sm_mhz_min": c["sm_min_mhz"], "power_w_max": c["power_w_max"], "reasons": c["reasons"],
             "gpu_launches": int(L.swec_kernel_launches() - launches0)}
 
@@ -671,7 +680,9 @@ def main():
         sev = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus + 1)]
         with ClockSampler(local, gpu_uuid) as sclk:
             sev[0].record()
+            lp_steps = []
             for i in range(n_sus):
+                lp_steps.append(power_state(L, local)[1])          # which variant this launch is about to take
                 step()
                 sev[i + 1].record()
             barrier()
@@ -686,7 +697,11 @@ def main():
                      "ms_every_10th_step": [round(x, 3) for x in sms[::10]], "ms_min": round(min(sms), 4),
                      "value": round(world * dat_size / (tail / 1e3) / 1e9, 2), "unit": UNIT,
                      "roofline_frac": round(1.4 * dat_size / (tail / 1e3) / 1e9 / load_peaks()[0], 4),
-                     "sm_mhz_min": sc["sm_min_mhz"], "power_w_max": sc["power_w_max"], "reasons": sc["reasons"]}
+                     "sm_mhz_min": sc["sm_min_mhz"], "power_w_max": sc["power_w_max"], "reasons": sc["reasons"],
+                     "power_mode": "auto: boost-clock kernel variant until the Horner kernels own > 45 % of the last "
+                                   "second, the low-power variant from then on",
+                     "low_power_variant_from_step": (lp_steps.index(1) if 1 in lp_steps else None),
+                     "heat_ms_at_end": round(power_state(L, local)[0], 1)}
     # ---- e2e leg: Encoder.Encode on pinned host buffers (H2D + kernel + D2H timed) -----------------
     e2e = None
     if not args.no_e2e:

@@ -824,7 +824,7 @@ def test_write_dat_device_is_the_inverse_of_the_striping(cuda, swec, oracle, dat
     e = ec.Encoder(10, 4, device=0)
     try:
         dat = oracle.synth(0, dat_size, SEED ^ dat_size)
-        shards = oracle.encode_dat_image(dat, large=large, small=small)
+        shards = oracle.encode_dat_image(dat, buffer_size=min(256 * 1024, small), large=large, small=small)
         assert (oracle.write_dat_image(shards, dat_size, large=large, small=small) == dat).all()
         dsh = [dev(torch, s_) for s_ in shards]
         out = torch.full((dat_size + 64,), 0xEE, dtype=torch.uint8, device="cuda")
