@@ -226,17 +226,26 @@ class FilePipeline {
         stats.items++;
         const int K = rows_.cols, R = rows_.rows;
         const size_t len = item.len;
+        // Every pread is cut into pieces of at most io_piece_ bytes so that ONE stripe keeps the whole I/O pool busy
+        // (k preads of 8 MiB are only k tasks; a thread copies 2-3 GB/s out of the page cache into cache-cold memory).
+        struct Piece { int op; size_t off, len; };
+        std::vector<Piece> rpieces;
+        for (size_t i = 0; i < item.reads.size(); i++)
+            for (size_t o = 0; o < item.reads[i].len; o += io_piece_)
+                rpieces.push_back({int(i), o, std::min(io_piece_, item.reads[i].len - o)});
         const std::function<int(int)> read_one = [&](int idx) -> int {
-            const ReadOp& r = item.reads[size_t(idx)];
-            uint8_t* dst = s->host + size_t(r.stream) * chunk_ + r.dst_off;
-            const size_t len = r.len;
+            const Piece& pc = rpieces[size_t(idx)];
+            const ReadOp& r = item.reads[size_t(pc.op)];
+            uint8_t* dst = s->host + size_t(r.stream) * chunk_ + r.dst_off + pc.off;
+            const int64_t off = r.off + int64_t(pc.off);
+            const size_t len = pc.len;
             // O_DIRECT: the device DMAs straight into the pinned slot; short counts only happen at EOF, where the
             // remainder (unaligned now) continues on the buffered descriptor
-            const int fd0 = direct_ok(r.dfd, r.off, len, dst) ? r.dfd : r.fd;
+            const int fd0 = direct_ok(r.dfd, off, len, dst) ? r.dfd : r.fd;
             size_t got = 0;
             while (got < len) {
-                const int fd = (fd0 == r.dfd && direct_ok(r.dfd, r.off + int64_t(got), len - got, dst + got)) ? r.dfd : r.fd;
-                const ssize_t n = pread(fd, dst + got, len - got, off_t(r.off + int64_t(got)));
+                const int fd = (fd0 == r.dfd && direct_ok(r.dfd, off + int64_t(got), len - got, dst + got)) ? r.dfd : r.fd;
+                const ssize_t n = pread(fd, dst + got, len - got, off_t(off + int64_t(got)));
                 if (n < 0) {
                     if (errno == EINTR) continue;
                     const int rc = io_fail("pread");
@@ -249,7 +258,7 @@ class FilePipeline {
             if (got < len) memset(dst + got, 0, len - got);
             return SWEC_OK;
         };
-        if (const int rrc = io_->parallel_for(int(item.reads.size()), read_one)) {
+        if (const int rrc = io_->parallel_for(int(rpieces.size()), read_one)) {
             set_last_error(noted_error());
             return set_error(rrc, s);
         }
@@ -399,13 +408,23 @@ class FilePipeline {
             const double tw1 = PipeStats::now();
             stats.wait_gpu += tw1 - tw0;   // writer thread only
             if (!rc) {
+                struct Piece { int op; size_t off, len; };
+                std::vector<Piece> wpieces;
+                // one task per shard file: buffered writes take the inode's lock exclusively, so pieces of the same
+                // file would only queue behind each other (SWEC_FILE_WRITE_PIECE splits them anyway, for O_DIRECT devices)
+                const size_t wpiece = std::max<size_t>(4096, env_sz("SWEC_FILE_WRITE_PIECE", s->item.len ? s->item.len : 4096) & ~size_t(4095));
+                for (size_t i = 0; i < s->item.writes.size(); i++)
+                    for (size_t o = 0; o < s->item.len; o += wpiece)
+                        wpieces.push_back({int(i), o, std::min(wpiece, s->item.len - o)});
                 const std::function<int(int)> write_one = [&](int idx) -> int {
-                    const WriteOp& w = s->item.writes[size_t(idx)];
-                    const uint8_t* src = s->host + size_t(w.stream) * chunk_;
+                    const Piece& pc = wpieces[size_t(idx)];
+                    const WriteOp& w = s->item.writes[size_t(pc.op)];
+                    const uint8_t* src = s->host + size_t(w.stream) * chunk_ + pc.off;
+                    const int64_t off = w.off + int64_t(pc.off);
                     size_t put = 0;
-                    while (put < s->item.len) {
-                        const int fd = direct_ok(w.dfd, w.off + int64_t(put), s->item.len - put, src + put) ? w.dfd : w.fd;
-                        const ssize_t n = pwrite(fd, src + put, s->item.len - put, off_t(w.off + int64_t(put)));
+                    while (put < pc.len) {
+                        const int fd = direct_ok(w.dfd, off + int64_t(put), pc.len - put, src + put) ? w.dfd : w.fd;
+                        const ssize_t n = pwrite(fd, src + put, pc.len - put, off_t(off + int64_t(put)));
                         if (n < 0) {
                             if (errno == EINTR) continue;
                             const int rc2 = io_fail("pwrite");
@@ -416,7 +435,7 @@ class FilePipeline {
                     }
                     return SWEC_OK;
                 };
-                rc = io_->parallel_for(int(s->item.writes.size()), write_one);
+                rc = io_->parallel_for(int(wpieces.size()), write_one);
                 if (rc) set_last_error(noted_error());
                 stats.write += PipeStats::now() - tw1;
             }
@@ -436,6 +455,7 @@ class FilePipeline {
     swec_encoder* enc_;
     Matrix rows_;
     size_t chunk_;
+    const size_t io_piece_ = std::max<size_t>(4096, env_sz("SWEC_FILE_IO_PIECE", size_t(2) << 20) & ~size_t(4095));
     double t_begin_ = 0;
     bool verify_ = false;
     unsigned long long* dev_bad_ = nullptr;
