@@ -781,7 +781,12 @@ def main():
                    "roofline": {"bound": "pcie_h2d", "achieved": round(e2e_steps * 10 * n / dt / 1e9, 2),
                                 "peak": round(h2d_peak, 2), "unit": "GB/s per GPU",
                                 "frac": round(e2e_steps * 10 * n / dt / 1e9 / h2d_peak, 4),
-                                "peak_source": "H2D-only DMA of the same pinned buffer, timed in this run"},
+                                "peak_source": "H2D-only DMA of the same pinned buffer, timed in this run",
+                                "host_ceiling": "with several GPUs the bound is the socket, not the link: plain cudaMemcpy in "
+                                                "both directions at once tops out at ~95 + 95 GB/s per socket on this pool's "
+                                                "hosts (profiles/r02d_pcie_probe_thp.jsonl: 23.7 GB/s per direction per GPU with 4 "
+                                                "GPUs on a socket); e2e moves 1.4 B of DMA per input byte, so ~136-142 GB/s of "
+                                                "input per socket is the ceiling (N=8: ~283)"},
                    "check": e2e_check}
             L.swec_free_pinned(raw)
     barrier()
