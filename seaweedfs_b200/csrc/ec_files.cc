@@ -103,6 +103,38 @@ struct Slot {
 };
 
 
+// ONE I/O pool per process, shared by every file pipeline: concurrent volumes (the shell runs up to 10 at once) must not
+// multiply the thread count — 4 pipelines x 16 threads on a 16-core cgroup quota ran at 8.5 GB/s where one volume alone
+// does 21 (profiles/r02e_files_multi_1gpu_4x4GiB.jsonl).  Size: the CPU time the process may actually use (cgroup quota,
+// else the hardware concurrency), between 4 and 64; SWEC_IO_THREADS overrides.  Leaked on purpose, like the other
+// process-wide helpers: threads must not be joined from static destructors.
+size_t usable_cpus() {
+    size_t n = std::max(1u, std::thread::hardware_concurrency());
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+        char q[32] = {0};
+        long long period = 0;
+        if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0)
+            n = std::min<size_t>(n, size_t(std::max<long long>(1, (atoll(q) + period - 1) / period)));
+        fclose(f);
+    } else {
+        long long quota = -1, period = 0;
+        if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+            if (fscanf(g, "%lld", &quota) != 1) quota = -1;
+            fclose(g);
+        }
+        if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+            if (fscanf(g, "%lld", &period) != 1) period = 0;
+            fclose(g);
+        }
+        if (quota > 0 && period > 0) n = std::min<size_t>(n, size_t(std::max<long long>(1, (quota + period - 1) / period)));
+    }
+    return n;
+}
+IoPool& file_io_pool() {
+    static IoPool* pool = new IoPool(env_sz("SWEC_IO_THREADS", std::min<size_t>(64, std::max<size_t>(4, usable_cpus()))));
+    return *pool;
+}
+
 // Staging rings outlive a call: pinning (mmap + mbind + cudaHostRegister) and un-pinning 3 x 14 x 8 MiB costs
 // 0.1-2 s per call (profiles/r01z_files_*), as much as the pipeline itself spends on an 8 GiB volume.  A volume
 // server encodes volume after volume, so finished pipelines park their ring here (per device and size, a few at
@@ -204,7 +236,7 @@ class FilePipeline {
             s.item = Item{};
             free_.push_back(&s);
         }
-        io_.reset(new IoPool(env_sz("SWEC_IO_THREADS", std::min<size_t>(16, std::max<size_t>(4, std::thread::hardware_concurrency() / 4)))));
+        io_ = &file_io_pool();
         writer_ = std::thread([this] { writer_loop(); });
         started_ = true;
         return SWEC_OK;
@@ -333,7 +365,7 @@ class FilePipeline {
         }
         cv_.notify_all();
         if (writer_.joinable()) writer_.join();
-        io_.reset();
+        io_ = nullptr;
         cudaSetDevice(enc_->device);
         bool healthy = error_ == 0;
         for (auto& s : slots_)
@@ -465,7 +497,7 @@ class FilePipeline {
     std::mutex mu_;
     std::condition_variable cv_;
     std::thread writer_;
-    std::unique_ptr<IoPool> io_;
+    IoPool* io_ = nullptr;  // the process-wide pool (not owned)
     int error_ = 0;
     std::string error_msg_;
     bool stop_ = false, started_ = false;
@@ -906,7 +938,7 @@ int swec_write_dat_file(const char* base, int64_t dat_size, const char* const* s
         if (st.st_size < pos[size_t(s2)]) return fail(SWEC_ERR_IO, "short read copying shard " + std::to_string(s2));
     }
     if (ftruncate(dat, off_t(dat_size)) != 0) return io_fail("size .dat");
-    IoPool pool(env_sz("SWEC_IO_THREADS", std::min<size_t>(16, std::max<size_t>(4, std::thread::hardware_concurrency() / 4))));
+    IoPool& pool = file_io_pool();
     std::mutex err_mu;
     std::string err_text;
     const std::function<int(int)> copy_piece = [&](int idx) -> int {
