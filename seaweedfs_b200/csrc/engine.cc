@@ -725,14 +725,24 @@ static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std
         StagingSlot& sl = e->slots[si];
         const uint8_t* din[SWEC_MAX_INPUTS];
         uint8_t* dout[SWEC_MAX_SHARDS];
-        for (int i = 0; i < K; i++) din[i] = sl.dev + size_t(i) * stride;
-        // the K input streams sit at pitch `stride` in both buffers: one strided DMA instead of K small ones
-        SWEC_CUDA(cudaMemcpy2DAsync(sl.dev, stride, sl.host, stride, fill, size_t(K), cudaMemcpyHostToDevice, sl.stream));
-        for (int r = 0; r < R; r++) dout[r] = sl.dev + size_t(K + r) * stride;
-        const int rc2 = e->apply(rows, din, dout, fill, Layout{}, sl.stream);
-        if (rc2) return rc2;
-        SWEC_CUDA(cudaMemcpy2DAsync(sl.host + size_t(K) * stride, stride, dout[0], stride, fill, size_t(R),
-                                    cudaMemcpyDeviceToHost, sl.stream));
+        const long zc_mode = g_opt_host_zero_copy.load();
+        if (sl.host_dev && (zc_mode == 1 || (zc_mode == 2 && fill <= size_t(g_opt_host_zero_copy_max.load())))) {
+            // needle-sized batches: the kernel works on the mapped ring itself — one launch instead of
+            // strided DMA in + launch + strided DMA out (what a degraded read waits for is API round trips)
+            for (int i = 0; i < K; i++) din[i] = sl.host_dev + size_t(i) * stride;
+            for (int r = 0; r < R; r++) dout[r] = sl.host_dev + size_t(K + r) * stride;
+            const int rc2 = e->apply(rows, din, dout, fill, Layout{}, sl.stream);
+            if (rc2) return rc2;
+        } else {
+            for (int i = 0; i < K; i++) din[i] = sl.dev + size_t(i) * stride;
+            // the K input streams sit at pitch `stride` in both buffers: one strided DMA instead of K small ones
+            SWEC_CUDA(cudaMemcpy2DAsync(sl.dev, stride, sl.host, stride, fill, size_t(K), cudaMemcpyHostToDevice, sl.stream));
+            for (int r = 0; r < R; r++) dout[r] = sl.dev + size_t(K + r) * stride;
+            const int rc2 = e->apply(rows, din, dout, fill, Layout{}, sl.stream);
+            if (rc2) return rc2;
+            SWEC_CUDA(cudaMemcpy2DAsync(sl.host + size_t(K) * stride, stride, dout[0], stride, fill, size_t(R),
+                                        cudaMemcpyDeviceToHost, sl.stream));
+        }
         SWEC_CUDA(cudaEventRecord(sl.done, sl.stream));
         sl.busy = true;
         fill = 0;
