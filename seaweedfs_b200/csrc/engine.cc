@@ -490,6 +490,7 @@ bool constant_pitch(const uint8_t* const* p, int n, size_t min_pitch, size_t* pi
     if (p[1] <= p[0]) return false;
     const size_t d = size_t(p[1] - p[0]);
     if (d < min_pitch) return false;
+    if (d > size_t(0x7fffffff)) return false;  // cudaMemcpy2D pitches are limited (cudaDevAttrMaxPitch): huge shards go one by one
     for (int i = 2; i < n; i++)
         if (p[i] != p[0] + size_t(i) * d) return false;
     *pitch = d;
