@@ -7,7 +7,10 @@
  *                             malloc'ed (pageable, Go-heap-like) buffers of N bytes, data read from IN
  *                             (10*N bytes), parity appended to OUT; then Encoder.Reconstruct with four nil
  *                             shards (rebuildEcFiles, ec_encoder.go:340-376) and ReconstructData with one
- *                             (store_ec.go:551), each compared with the originals
+ *                             (store_ec.go:551), each compared with the originals; then the same Encode on the
+ *                             pinned batch buffers of swecAllocShardBuffers (ONE swec_alloc_pinned_for_device
+ *                             allocation cut into 14 slices: zero-copy kernel / strided DMA), the device order
+ *                             swecPickDevice walks, and the decode-kernel cache statistics
  *
  * Compiled by tests/test_c_harness.py with  gcc -std=c11 -Wall -Wextra -Werror -pedantic  — which is also
  * the check that the header is valid C, not just C++.  Test infrastructure; not part of the product.   */
@@ -92,6 +95,11 @@ static int run_abi(void) {
     int nre = -1;
     CHECK(swec_rebuild_ec_files("/nonexistent/1", NULL, 0, K, M, 0, rebuilt, &nre) == SWEC_ERR_TOO_FEW_SHARDS);
     CHECK(nre == 0);
+    /* round-2 entry points, host-only behaviour */
+    int aot = 0;
+    CHECK(swec_jit_stats(NULL, NULL, &aot, NULL) == SWEC_OK && aot == 15);
+    CHECK(swec_set_option("host_zero_copy", 2) == SWEC_OK && swec_set_option("host_zero_copy", 3) == SWEC_ERR_INVALID_ARG);
+    CHECK(swec_set_option("file_direct_io", 0) == SWEC_OK && swec_set_option("power_mode", 0) == SWEC_OK);
     swec_shutdown();
     swec_shutdown(); /* idempotent */
     return fails;
@@ -168,6 +176,44 @@ static int run_encode(const char *in_path, const char *out_path, size_t n) {
     memset(present, 1, sizeof present);
     for (int i = 0; i < 5; i++) present[i] = 0;
     CHECK(swec_reconstruct(enc, shards, present, n, 0) == SWEC_ERR_TOO_FEW_SHARDS);
+
+    /* swecAllocShardBuffers (integration/go/ec_swec.go): the batch buffers of encodeDatFile / rebuildEcFiles as 14
+     * slices of ONE pinned allocation at a 4 KiB-rounded pitch; Encode on them must give the pageable call's parity,
+     * and a single lost shard must come back through the compiled-in reconstruct kernel (no NVRTC) */
+    {
+        const size_t pitch = (n + 4095) & ~(size_t)4095;
+        uint8_t *base = swec_alloc_pinned_for_device(0, T * pitch);
+        CHECK(base != NULL);
+        if (base) {
+            uint8_t *pin[T];
+            for (int i = 0; i < T; i++) {
+                pin[i] = base + (size_t)i * pitch;
+                if (i < K) memcpy(pin[i], data + (size_t)i * n, n);
+                else memset(pin[i], 0xEE, n);
+            }
+            CHECK(swec_encode(enc, pin, n) == SWEC_OK);
+            for (int i = 0; i < T; i++) CHECK(memcmp(pin[i], orig[i], n) == 0);
+            uint64_t aot0 = 0, aot1 = 0;
+            int aot_matrices = 0;
+            CHECK(swec_jit_stats(NULL, NULL, &aot_matrices, &aot0) == SWEC_OK && aot_matrices == 15);
+            memset(present, 1, sizeof present);
+            present[7] = 0;
+            memset(pin[7], 0x33, n);
+            CHECK(swec_reconstruct(enc, pin, present, n, 1) == SWEC_OK);
+            CHECK(memcmp(pin[7], orig[7], n) == 0);
+            CHECK(swec_jit_stats(NULL, NULL, NULL, &aot1) == SWEC_OK);
+            CHECK(aot1 == aot0 + 1); /* one launch of the compiled-in single-loss kernel (a <16 B tail adds the byte kernel) */
+            swec_free_pinned(base);
+        }
+        int order[64], cnt = 0;
+        CHECK(swec_device_spread_order(order, 64, &cnt) == SWEC_OK && cnt == ndev);
+        int seen = 0;
+        for (int i = 0; i < cnt; i++) seen += order[i] >= 0 && order[i] < ndev;
+        CHECK(seen == ndev);
+        double heat = -1;
+        int lp = -1;
+        CHECK(swec_debug_power_state(0, &heat, &lp) == SWEC_OK && heat >= 0 && (lp == 0 || lp == 1));
+    }
 
     CHECK(swec_kernel_launches() > 0);
     swec_encoder_free(enc);
