@@ -727,7 +727,10 @@ static int apply_host_packed(swec_encoder_impl* e, const Matrix& rows, const std
         const uint8_t* din[SWEC_MAX_INPUTS];
         uint8_t* dout[SWEC_MAX_SHARDS];
         const long zc_mode = g_opt_host_zero_copy.load();
-        if (sl.host_dev && (zc_mode == 1 || (zc_mode == 2 && fill <= size_t(g_opt_host_zero_copy_max.load())))) {
+        // measured (profiles/r02g_needle_reads.jsonl vs r02c_): zero-copy is worth +5 % for one needle per call and costs
+        // 35 % when 1,600 needles fill slot after slot — full slots keep the strided-DMA pipeline
+        const size_t packed_zero_copy_max = std::min(size_t(g_opt_host_zero_copy_max.load()), size_t(256) << 10);
+        if (sl.host_dev && (zc_mode == 1 || (zc_mode == 2 && fill <= packed_zero_copy_max))) {
             // needle-sized batches: the kernel works on the mapped ring itself — one launch instead of
             // strided DMA in + launch + strided DMA out (what a degraded read waits for is API round trips)
             for (int i = 0; i < K; i++) din[i] = sl.host_dev + size_t(i) * stride;
