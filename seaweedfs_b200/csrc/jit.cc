@@ -165,19 +165,28 @@ bool jit_cached(swec_encoder_impl* enc, const Matrix& rows) {
 // ---- on-disk cubin cache -------------------------------------------------------------------------------------
 namespace {
 
+bool cache_dir_trusted(const std::string& dir);
+
 std::string disk_cache_dir() {
     if (getenv("SWEC_NO_DISK_CACHE")) return "";
-    if (const char* d = getenv("SWEC_CACHE_DIR")) return *d ? std::string(d) : "";
-    if (const char* x = getenv("XDG_CACHE_HOME"))
-        if (*x) return std::string(x) + "/swec";
-    if (const char* h = getenv("HOME"))
-        if (*h) return std::string(h) + "/.cache/swec";
-    return "";
+    std::string dir;
+    if (const char* d = getenv("SWEC_CACHE_DIR")) dir = d;
+    else if (const char* x = getenv("XDG_CACHE_HOME"); x && *x) dir = std::string(x) + "/swec";
+    else if (const char* h = getenv("HOME"); h && *h) dir = std::string(h) + "/.cache/swec";
+    return !dir.empty() && cache_dir_trusted(dir) ? dir : "";
 }
 
 void mkdir_p(const std::string& dir) {
     for (size_t i = 1; i <= dir.size(); i++)
-        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), i == dir.size() ? 0700 : 0755);
+}
+
+// A cubin is executable code: only a directory that belongs to this user and that nobody else can write to is
+// trusted as a cache (the same rule ssh applies to ~/.ssh).  Anything else disables the cache, never the engine.
+bool cache_dir_trusted(const std::string& dir) {
+    struct stat st;
+    if (stat(dir.c_str(), &st) != 0) return true;  // does not exist yet: we create it 0700
+    return S_ISDIR(st.st_mode) && st.st_uid == geteuid() && (st.st_mode & (S_IWGRP | S_IWOTH)) == 0;
 }
 
 // 128 bits of FNV-1a (two different offsets) over the text that determines the cubin

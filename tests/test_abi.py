@@ -276,7 +276,13 @@ def test_cubin_disk_cache_and_aot_table(swec, tmp_path, monkeypatch):
     assert len(files) == 1 and files[0].stat().st_size == size
     rc, size2, compiles, hits, dt = compile_once()
     assert rc == 0 and (compiles, hits) == (0, 1) and size2 == size and dt < 0.1, dt
-    # a truncated file in the cache is not fatal for loading paths; the debug entry just reports what it read
+    # a cache directory that others can write to is not trusted with executable code: the cache is off, NVRTC compiles
+    os.chmod(tmp_path / "cubins", 0o777)
+    rc, _, compiles, hits, _ = compile_once()
+    assert rc == 0 and (compiles, hits) == (1, 0)
+    os.chmod(tmp_path / "cubins", 0o700)
+    rc, _, compiles, hits, _ = compile_once()
+    assert rc == 0 and (compiles, hits) == (0, 1)
     monkeypatch.setenv("SWEC_NO_DISK_CACHE", "1")
     rc, _, compiles, hits, _ = compile_once()
     assert rc == 0 and (compiles, hits) == (1, 0)
