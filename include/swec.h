@@ -103,7 +103,8 @@ int swec_debug_power_state(int device, double *heat_ms, int *low_power);
 /* The decode-kernel cache (GPU analogue of the decode-matrix LRU, rse/src/core.rs:25,700-734), three tiers:
  * `aot_matrices` reconstruct matrices compiled with the library (every single-shard loss of RS(10,4) and shards 0-3
  * lost: no compile, no NVRTC, any stream length); an on-disk cubin cache shared by every process
- * ($SWEC_CACHE_DIR, else $XDG_CACHE_HOME/swec, else ~/.cache/swec; SWEC_NO_DISK_CACHE=1 disables) whose hits are
+ * ($SWEC_CACHE_DIR, else $XDG_CACHE_HOME/swec, else ~/.cache/swec; SWEC_NO_DISK_CACHE=1 disables; a directory that does
+ * not belong to the calling user or that group/others can write to is not trusted with executable code and is ignored) whose hits are
  * counted in `disk_cache_hits`; NVRTC for patterns never seen before (`nvrtc_compiles`).  `aot_launches` = launches of
  * the compiled-in reconstruct kernels by this process.  Any pointer may be NULL. */
 int swec_jit_stats(uint64_t *nvrtc_compiles, uint64_t *disk_cache_hits, int *aot_matrices,

@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -60,7 +61,8 @@ bool read_all(const std::string& path, std::vector<uint8_t>* out) {
 // the new EOF: SIGBUS, which kills the whole volume server where the reference's ReadAt only returns an error.
 // With rename() existing mappings keep the old inode and its bytes until they are unmapped.
 bool write_all(const std::string& path, const std::vector<uint8_t>& data) {
-    const std::string tmp = path + ".tmp." + std::to_string(long(getpid()));
+    static std::atomic<unsigned> serial{0};  // two threads of one process may rewrite the same path
+    const std::string tmp = path + ".tmp." + std::to_string(long(getpid())) + "." + std::to_string(serial++);
     const int fd = open(tmp.c_str(), O_TRUNC | O_CREAT | O_WRONLY, 0644);
     if (fd < 0) return false;
     size_t put = 0;
