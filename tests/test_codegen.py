@@ -95,3 +95,113 @@ def test_random_and_degenerate_matrices(tool):
     run_case(tool, np.zeros((2, 3)))
     run_case(tool, np.eye(4))
     run_case(tool, [[1, 2, 4, 8, 16, 32, 64, 128], [255] * 8])
+
+
+AOT_HARNESS = r"""
+#include <cstdint>
+#include <cstdio>
+typedef uint32_t u32;
+#define __device__
+#define __forceinline__ inline
+#define SWEC_X2(a,b) ((a)^(b))
+#define SWEC_X3(a,b,c) ((a)^(b)^(c))
+static inline u32 xt(u32 a){ u32 hi=a&0x80808080u; return ((a^hi)<<1) ^ ((hi>>7)*0x1du); }
+#define SWEC_XT0A(a) xt(a)
+#define SWEC_XT0B(a) xt(a)
+#define SWEC_XT1A(a,s) (xt(a)^(s))
+#define SWEC_XT1B(a,s) (xt(a)^(s))
+#include "gen_aot_recon.inc"
+#include "gen_aot_recon_keys.inc"
+template <class G> static void run(int idx) {
+  u32 x[G::K], y[G::R];
+  unsigned long long s = 88172645463325252ull + idx;
+  for (int it = 0; it < 512; it++) {
+    for (int i = 0; i < G::K; i++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x[i] = (u32)(s >> 16); }
+    if (it == 0) for (int i = 0; i < G::K; i++) x[i] = 0xffffffffu;
+    G::combine(x, y);
+    fwrite(x, 4, G::K, stdout); fwrite(y, 4, G::R, stdout);
+  }
+}
+int main(int argc, char** argv){
+  if (argc > 1) {  // dump the key table: r k coefficients...
+    for (int i = 0; i < SWEC_AOT_RECON_COUNT; i++) {
+      printf("%d %d", kAotReconKeys[i].r, kAotReconKeys[i].k);
+      for (int j = 0; j < kAotReconKeys[i].r * kAotReconKeys[i].k; j++) printf(" %d", kAotReconKeys[i].c[j]);
+      printf("\n");
+    }
+    return 0;
+  }
+#define RUN(I) run<SwecAotRecon##I>(I);
+  SWEC_AOT_RECON_FOREACH(RUN)
+  return 0;
+}
+"""
+
+
+def test_compiled_in_reconstruct_matrices(tool):
+    """aot_recon.cu's inputs (codegen_main.cc --aot-recon 10 4): the matrix table is exactly the fused reconstruct
+    matrix of every single-shard loss and of shards 0-3 lost (oracle: rs_numpy.fused_reconstruct_rows, the statement of
+    rse/src/core.rs:736-926), in that order, and every emitted combiner computes its matrix."""
+    from oracle import rs_numpy as rn
+    d, exe = tool
+    for emit, name in (("structs", "gen_aot_recon.inc"), ("keys", "gen_aot_recon_keys.inc")):
+        out = subprocess.run([exe, "--aot-recon", "10", "4", "--emit", emit], check=True, stdout=subprocess.PIPE, text=True).stdout
+        (d / name).write_text(out)
+    (d / "aot.cc").write_text(AOT_HARNESS)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(d / "aot"), str(d / "aot.cc")], check=True, cwd=d)
+    keys = []
+    for line in subprocess.run([str(d / "aot"), "keys"], check=True, stdout=subprocess.PIPE, text=True).stdout.splitlines():
+        f = [int(v) for v in line.split()]
+        keys.append(np.array(f[2:], dtype=np.uint8).reshape(f[0], f[1]))
+    patterns = [(i,) for i in range(14)] + [(0, 1, 2, 3)]
+    assert len(keys) == len(patterns) == 15
+    for lost, key in zip(patterns, keys):
+        _, outs, rows = rn.fused_reconstruct_rows(10, 4, [i not in lost for i in range(14)])
+        assert list(outs) == list(lost) and (np.asarray(rows, dtype=np.uint8) == key).all(), lost
+    raw = subprocess.run([str(d / "aot")], check=True, stdout=subprocess.PIPE).stdout
+    words = np.frombuffer(raw, dtype="<u4")
+    pos = 0
+    for key in keys:
+        r, k = key.shape
+        blk = words[pos:pos + 512 * (k + r)].reshape(512, k + r)
+        pos += 512 * (k + r)
+        x = blk[:, :k].copy().view(np.uint8).reshape(-1, k, 4)
+        y = blk[:, k:].copy().view(np.uint8).reshape(-1, r, 4)
+        want = np.zeros_like(y)
+        for p in range(r):
+            for i in range(k):
+                want[:, p, :] ^= rn.MUL[int(key[p, i])][x[:, i, :]]
+        assert (want == y).all()
+    assert pos == len(words)
+
+
+XT_HARNESS = r"""
+#include <cstdint>
+#include <cstdio>
+typedef uint32_t u32; typedef uint64_t u64;
+static inline u32 ref(u32 a, u32 s){ u32 hi=a&0x80808080u; return (((a^hi)<<1) ^ ((hi>>7)*0x1du)) ^ s; }
+// variant 0 of device_common.cuh, instruction by instruction: LOP, IMAD.HI, IMAD, IMAD, LOP3
+static inline u32 v0(u32 a, u32 s){ u32 hi=a&0x80808080u; u32 m=(u32)(((u64)hi*0x3a000000ull)>>32); u32 a2=a*2u; u32 b2=hi*0xfffffffeu+a2; return b2^m^s; }
+// variant 2: PRMT with selector 0xba98 (bytes 0-3 of a, sign-replicated), IMAD.SHL, two LOP3 0x6a = (x & c) ^ z
+static inline u32 prmt_sign(u32 a){ u32 r=0; for(int b=0;b<4;b++) if((a>>(8*b))&0x80u) r|=0xffu<<(8*b); return r; }
+static inline u32 v2(u32 a, u32 s){ u32 mask=prmt_sign(a); u32 a2=a*2u; u32 u=(a2&0xfefefefeu)^s; return (mask&0x1d1d1d1du)^u; }
+int main(){
+  u64 st=0x9E3779B97F4A7C15ull; long bad=0;
+  for(long it=0; it<4000000; it++){
+    st^=st<<13; st^=st>>7; st^=st<<17; u32 a=(u32)(st>>11), s=(u32)(st>>37)*2654435761u;
+    if(it<65536){ a=(u32)it*0x00010001u; }            // every 16-bit pattern in both halves
+    if(ref(a,s)!=v0(a,s) || ref(a,s)!=v2(a,s)) bad++;
+  }
+  printf("%ld\n", bad); return bad!=0;
+}
+"""
+
+
+def test_both_multiply_by_two_spellings_equal_xtime(tmp_path):
+    """The two instruction mixes of the SWAR multiply-by-2 step (device_common.cuh: variant 0 = IMAD.HI reduction
+    mask + 2 IMAD shift, variant 2 = PRMT sign mask), restated instruction by instruction in C, equal the plain
+    xtime on four packed bytes for 4 M random words and every 16-bit pattern."""
+    (tmp_path / "xt.cc").write_text(XT_HARNESS)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(tmp_path / "xt"), str(tmp_path / "xt.cc")], check=True)
+    r = subprocess.run([str(tmp_path / "xt")], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout
