@@ -90,7 +90,9 @@ uint64_t swec_kernel_launches(void);          /* kernels this process has launch
  * host-buffer calls of at most "host_zero_copy_max" bytes per shard run the kernel directly on the (mapped, pinned) host
  * memory over PCIe instead of staging through HBM}, "file_direct_io" {bit 0: O_DIRECT reads, bit 1: O_DIRECT writes in
  * the file-level entry points}.  Measurement knobs: "xt_variant" {0..3} (instruction mix of run-time specialised kernels,
- * device_common.cuh), "use_aot" {0,1} (0: RS(10,4) encode is specialised at run time like any matrix).     */
+ * device_common.cuh), "use_aot" {0,1} (0: RS(10,4) encode is specialised at run time like any matrix), "jit_share_powers"
+ * {0,1} (1: run-time specialised kernels are generated with shared power chains — fewer multiply-by-2 steps; CPU-verified,
+ * not yet measured on a B200, hence off).                                                                          */
 int swec_set_option(const char *name, long value);
 /* Diagnostics: generate and NVRTC-compile (sm_100a) the specialised kernel for an r×k matrix without
  * loading it — needs no GPU.  Reports the cubin size and the generator's instruction statistics.  */

@@ -203,6 +203,70 @@ std::string generate_combine(const Matrix& rows, const std::string& struct_name,
     stats.shared_signals = int(shared.size());
     for (const Set& s : sets) stats.terms_after += int(s.sig.size());
 
+    // ---- 3b. shared power chains (opt.share_powers) -----------------------------------------------
+    // Horner on the OUTPUT side costs one multiply-by-2 step per degree of every row.  When the high bit-planes of
+    // several rows hold nothing but one and the same signal sigma (RS(10,4): the two pair-sum rows of the basis are
+    // c * (x0^...^x7) plus degree-0 terms), it is cheaper to build the powers 2^b * sigma ONCE on the input side and XOR
+    // the ones each row needs: rows q1 (degree 4) and q3 (degree 5) of the encode matrix share one 5-step chain
+    // instead of paying 4 + 5 steps.  Greedy over signals; a signal moves out of a row only above the degree of the
+    // row's other terms (below it the term rides in a Horner step for free).
+    std::vector<std::vector<std::pair<int, int>>> power_terms(static_cast<size_t>(R));  // per row: (signal, exponent)
+    std::map<int, int> power_need;                                                      // signal -> longest chain
+    if (opt.share_powers) {
+        auto set_ref = [&](int q, int b) -> Set* {
+            for (Set& s : sets)
+                if (s.q == q && s.b == b) return &s;
+            return nullptr;
+        };
+        auto row_degree = [&](int q, int without) {  // highest non-empty plane, ignoring `without` at planes >= 1
+            int d = -1;
+            for (const Set& s : sets) {
+                if (s.q != q) continue;
+                size_t n = s.sig.size();
+                if (without >= 0 && s.b >= 1 && std::find(s.sig.begin(), s.sig.end(), without) != s.sig.end()) n--;
+                if (n > 0) d = std::max(d, s.b);
+            }
+            return d;
+        };
+        const int nsig = K + int(shared.size());
+        for (;;) {
+            double best_gain = 0;
+            int best_sig = -1;
+            for (int sg = 0; sg < nsig; sg++) {
+                int steps_saved = 0, chain = power_need.count(sg) ? power_need[sg] : 0, chain_new = chain, moved = 0;
+                for (int q = 0; q < R; q++) {
+                    const int before = row_degree(q, -1), after = std::max(0, row_degree(q, sg));
+                    if (before <= after) continue;
+                    steps_saved += before - after;
+                    for (int b = after + 1; b <= before; b++) {
+                        const Set* st = set_ref(q, b);
+                        if (st && std::find(st->sig.begin(), st->sig.end(), sg) != st->sig.end()) {
+                            moved++;
+                            chain_new = std::max(chain_new, b);
+                        }
+                    }
+                }
+                // a step is ~5 instructions, an XORed power term ~half a LOP3; moved terms used to ride for free
+                const double gain = 5.0 * (steps_saved - (chain_new - chain)) - 0.5 * moved;
+                if (gain > best_gain + 1e-9) { best_gain = gain; best_sig = sg; }
+            }
+            if (best_sig < 0) break;
+            for (int q = 0; q < R; q++) {
+                const int before = row_degree(q, -1), after = std::max(0, row_degree(q, best_sig));
+                if (before <= after) continue;
+                for (int b = after + 1; b <= before; b++) {
+                    Set* st = set_ref(q, b);
+                    if (!st) continue;
+                    auto it = std::find(st->sig.begin(), st->sig.end(), best_sig);
+                    if (it == st->sig.end()) continue;
+                    st->sig.erase(it);
+                    power_terms[size_t(q)].push_back({best_sig, b});
+                    power_need[best_sig] = std::max(power_need[best_sig], b);
+                }
+            }
+        }
+    }
+
     // ---- 4. emit ---------------------------------------------------------------------------
     Emitter em;
     em.st = &stats;
@@ -222,15 +286,32 @@ std::string generate_combine(const Matrix& rows, const std::string& struct_name,
         else em.os << "SWEC_X2(" << name(sh[0]) << ", " << name(sh[1]) << ");\n";
         stats.xor_ops++;
     }
+    auto power_name = [&](int sig, int b) { return "p" + std::to_string(sig) + "_" + std::to_string(b); };
+    for (const auto& kv : power_need) {  // 2^b * sigma for b = 1 .. longest use
+        std::string prev = name(kv.first);
+        for (int b = 1; b <= kv.second; b++) {
+            stats.xtime_steps++;
+            em.os << "    const u32 " << power_name(kv.first, b) << " = SWEC_XT0" << ((stats.xtime_steps & 1) ? "B" : "A") << "(" << prev << ");\n";
+            prev = power_name(kv.first, b);
+        }
+    }
     std::vector<std::string> vname(static_cast<size_t>(R));
     for (int q = 0; q < R; q++) {
-        const int deg = vrows[size_t(q)].degree();
-        if (deg < 0) { vname[size_t(q)] = "0u"; continue; }
+        static const Set kEmpty{0, 0, {}};
         auto set_of = [&](int b) -> const Set& {
             for (const Set& s : sets)
                 if (s.q == q && s.b == b) return s;
-            return sets[0];
+            return kEmpty;
         };
+        int deg = -1;  // highest plane that still has terms (shared power chains may have emptied the top ones)
+        for (const Set& s : sets)
+            if (s.q == q && !s.sig.empty()) deg = std::max(deg, s.b);
+        std::vector<std::string> extra;  // powers of shared signals this row takes from the input-side chains
+        for (const auto& pt : power_terms[size_t(q)]) extra.push_back(power_name(pt.first, pt.second));
+        if (deg < 0) {
+            vname[size_t(q)] = extra.empty() ? "0u" : em.xor_all(extra);
+            continue;
+        }
         std::vector<std::string> terms;
         for (int sg : set_of(deg).sig) terms.push_back(name(sg));
         std::string acc = em.xor_all(terms);
@@ -266,6 +347,10 @@ std::string generate_combine(const Matrix& rows, const std::string& struct_name,
                 }
             }
             acc = nxt;
+        }
+        if (!extra.empty()) {
+            extra.insert(extra.begin(), acc);
+            acc = em.xor_all(extra);
         }
         vname[size_t(q)] = acc;
     }

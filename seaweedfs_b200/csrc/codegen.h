@@ -35,6 +35,10 @@ struct CodegenStats {
 struct CodegenOptions {
     bool optimise_basis = true;
     bool extract_common = true;
+    // input-side power chains for signals that alone occupy the high bit-planes of several rows (codegen.cc 3b).
+    // Off by default: the kernels it produces have been verified on the CPU only (tests/test_codegen.py), not yet
+    // measured on a B200 — "encode_formulation" / SWEC_ENCODE_FORMULATION=1 selects the RS(10,4) encode kernel built with it.
+    bool share_powers = false;
 };
 
 // Returns CUDA source text defining

@@ -887,6 +887,7 @@ int swec_set_option(const char* name, long value) {
     else if (n == "jit" && (value == 0 || value == 1)) g_opt_jit_enabled = value;
     else if (n == "xt_variant" && value >= 0 && value <= 3) g_opt_xt_variant = value;
     else if (n == "use_aot" && (value == 0 || value == 1)) g_opt_use_aot = value;
+    else if (n == "jit_share_powers" && (value == 0 || value == 1)) g_opt_jit_share_powers = value;
     else if (n == "power_mode" && value >= 0 && value <= 2) g_opt_power_mode = value;
     else return fail(SWEC_ERR_INVALID_ARG, "unknown option or value out of range: " + n);
     return SWEC_OK;

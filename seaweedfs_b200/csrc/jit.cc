@@ -239,7 +239,9 @@ static std::string jit_source(const Matrix& rows, int threads, int unroll, int v
     const std::string T = std::to_string(threads), U = std::to_string(unroll);
     std::string src = "#define SWEC_XT_VARIANT " + std::to_string(variant) + "\n";
     src += kDeviceCommonSrc;
-    src += generate_combine(rows, "SwecJit", CodegenOptions{}, stats);
+    CodegenOptions copt;
+    copt.share_powers = g_opt_jit_share_powers.load() != 0;  // off by default (kernels.h); the source text keys the cubin cache
+    src += generate_combine(rows, "SwecJit", copt, stats);
     src +=
         "extern \"C\" __global__ void __launch_bounds__(" + T + ") swec_jit_flat(const __grid_constant__ SwecApplyParams p) {\n"
         "    swec_horner_body<SwecJit, false, " + U + ">(p);\n}\n"

@@ -247,6 +247,7 @@ std::atomic<long> g_opt_enc_unroll{env_long("SWEC_ENC_UNROLL", 2)};
 std::atomic<long> g_opt_ctas_per_sm{env_long("SWEC_CTAS_PER_SM", 0)};  // 0 = derive from the shape
 std::atomic<long> g_opt_xt_variant{env_long("SWEC_XT_VARIANT_JIT", SWEC_XT_VARIANT)};
 std::atomic<long> g_opt_use_aot{env_long("SWEC_USE_AOT", 1)};
+std::atomic<long> g_opt_jit_share_powers{env_long("SWEC_JIT_SHARE_POWERS", 0)};
 std::atomic<long> g_opt_power_mode{env_long("SWEC_POWER_MODE", 0)};
 
 // ---- power policy: "heat" = kernel milliseconds recently spent on the device, decaying with a 1 s time

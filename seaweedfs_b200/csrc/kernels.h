@@ -16,6 +16,9 @@ extern std::atomic<long> g_opt_enc_threads, g_opt_enc_unroll, g_opt_ctas_per_sm;
 // measurement knobs: xtime instruction-mix variant of run-time specialised kernels (device_common.cuh), and
 // whether RS(10,4) encode takes the ahead-of-time kernel (1) or is specialised at run time like any matrix (0)
 extern std::atomic<long> g_opt_xt_variant, g_opt_use_aot;
+// measurement knob: run-time specialised kernels are generated with shared power chains (codegen.h share_powers): fewer
+// multiply-by-2 steps (RS(10,4) encode 24 -> 20, worst-case decode 27 -> 21); verified on the CPU, not yet measured on a B200
+extern std::atomic<long> g_opt_jit_share_powers;
 // Power policy (profiles/r01z_xt_variant_probe*.jsonl).  A B200 that encodes back to back for
 // more than a few hundred ms runs into its 1,000 W cap and drops the SM clock to ~1.45 GHz; from then on the
 // 4-instruction multiply-by-2 step (variant 2: fewer instructions, far fewer IMADs) is 4-5 % FASTER than the

@@ -235,6 +235,15 @@ def test_jit_source_compiles_for_sm100a_without_gpu(swec):
         assert rc == 0, L.swec_last_error()
         assert size.value > 1000 and steps.value <= 7 * rows.shape[0]
         print(rows.shape, size.value, steps.value, xors.value, round(time.perf_counter() - t0, 3))
+    # the opt-in formulation with shared power chains compiles too, with fewer steps for the worst-case decode matrix
+    assert L.swec_set_option(b"jit_share_powers", 1) == 0
+    try:
+        rows = np.ascontiguousarray(cases[0], dtype=np.uint8)
+        size, steps, xors = C.c_size_t(0), C.c_int(0), C.c_int(0)
+        assert L.swec_debug_jit_compile(4, 10, rows.ctypes.data, C.byref(size), C.byref(steps), C.byref(xors)) == 0
+        assert size.value > 1000 and steps.value == 21
+    finally:
+        assert L.swec_set_option(b"jit_share_powers", 0) == 0
 
 
 def test_device_spread_order_without_devices(swec):

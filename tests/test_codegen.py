@@ -205,3 +205,30 @@ def test_both_multiply_by_two_spellings_equal_xtime(tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(tmp_path / "xt"), str(tmp_path / "xt.cc")], check=True)
     r = subprocess.run([str(tmp_path / "xt")], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout
+
+
+def test_shared_power_chains_option(tool):
+    """codegen.h share_powers (off by default): input-side power chains for a signal that alone occupies the high
+    bit-planes of several rows.  Same bytes as the matrix product for the encode matrix, decode matrices, other ratios and
+    random / degenerate matrices; fewer multiply-by-2 steps where the structure exists (encode 24 -> 20, worst-case
+    decode 27 -> 21), never more."""
+    from oracle import rs_numpy as rn
+
+    def steps(gen):
+        return int(gen.strip().splitlines()[-1].split("xtime_steps=")[1].split()[0])
+    enc = rn.build_matrix(10, 14)[10:]
+    assert steps(run_case(tool, enc)) == 24 and steps(run_case(tool, enc, extra=("--share-powers",))) == 20
+    for lost in [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 10, 11), (5,), (12,), (9, 13), (2, 6, 11, 12), (1, 5, 13)]:
+        _, _, rows = rn.fused_reconstruct_rows(10, 4, [i not in lost for i in range(14)])
+        a, b = steps(run_case(tool, rows)), steps(run_case(tool, rows, extra=("--share-powers",)))
+        assert b <= a, (lost, a, b)
+        if lost == (0, 1, 2, 3):
+            assert (a, b) == (27, 21)
+    rng = np.random.default_rng(4)
+    for r, k in ((1, 1), (1, 10), (4, 3), (3, 17), (8, 10), (5, 32)):
+        run_case(tool, rng.integers(0, 256, (r, k)), extra=("--share-powers",))
+    for m in (np.zeros((2, 3)), np.eye(4), rn.build_matrix(6, 9)[6:], rn.build_matrix(20, 28)[20:],
+              [[1, 2, 4, 8, 16, 32, 64, 128], [255] * 8], [[0x16] * 8 + [1, 0], [0x34] * 8 + [0, 1]]):
+        run_case(tool, m, extra=("--share-powers",))
+        run_case(tool, m, extra=("--share-powers", "--no-basis"))
+        run_case(tool, m, extra=("--share-powers", "--no-cse"))
