@@ -107,7 +107,9 @@ std::string generate_combine(const Matrix& rows, const std::string& struct_name,
     // ---- 1. output basis ------------------------------------------------------------------
     std::vector<unsigned> masks(static_cast<size_t>(R));
     for (int p = 0; p < R; p++) masks[size_t(p)] = 1u << p;
-    if (opt.optimise_basis && R >= 2 && R <= 4) {
+    if (int(opt.basis.size()) == R && independent(opt.basis)) {
+        masks = opt.basis;
+    } else if (opt.optimise_basis && R >= 2 && R <= 4) {
         // exhaustive: choose R independent non-zero combinations with the least total cost
         const unsigned ncomb = (1u << R) - 1;
         std::vector<double> cost(ncomb + 1, 0.0);

@@ -20,6 +20,7 @@
 // NVRTC-specialised reconstruct kernels (run time).
 #pragma once
 #include <string>
+#include <vector>
 
 #include "gf256.h"
 
@@ -39,6 +40,10 @@ struct CodegenOptions {
     // Off by default: the kernels it produces have been verified on the CPU only (tests/test_codegen.py), not yet
     // measured on a B200 — "encode_formulation" / SWEC_ENCODE_FORMULATION=1 selects the RS(10,4) encode kernel built with it.
     bool share_powers = false;
+    // explicit output basis: R masks over the rows (bit p = row p takes part), GF(2)-independent; empty = choose one.
+    // Used by `swec_codegen --search-basis`, which tries every basis under the full cost (steps AND XORs after CSE and
+    // power sharing) instead of the a-priori estimate the built-in choice uses.
+    std::vector<unsigned> basis;
 };
 
 // Returns CUDA source text defining

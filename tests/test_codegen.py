@@ -232,3 +232,24 @@ def test_shared_power_chains_option(tool):
         run_case(tool, m, extra=("--share-powers",))
         run_case(tool, m, extra=("--share-powers", "--no-basis"))
         run_case(tool, m, extra=("--share-powers", "--no-cse"))
+
+
+def test_basis_search_over_the_emitted_cost(tool):
+    """`swec_codegen --search-basis`: every GF(2)-independent output basis judged by what the generator actually emits
+    (steps and XORs after CSE and power sharing) instead of the a-priori estimate.  Same bytes; RS(10,4) encode goes from
+    24 steps + 30 XORs (shipped) to 20 + 32 with shared power chains, shards 0,1,10,11 lost from 26 + 30 to 21 + 28."""
+    from oracle import rs_numpy as rn
+
+    def stats(gen):
+        last = gen.strip().splitlines()[-1]
+        return int(last.split("xtime_steps=")[1].split()[0]), int(last.split("xor_ops=")[1].split()[0])
+    enc = rn.build_matrix(10, 14)[10:]
+    assert stats(run_case(tool, enc)) == (24, 30)
+    assert stats(run_case(tool, enc, extra=("--search-basis",))) == (24, 27)
+    assert stats(run_case(tool, enc, extra=("--share-powers", "--search-basis"))) == (20, 32)
+    for lost, want in (((0, 1, 10, 11), (21, 28)), ((0, 1, 2, 3), (21, 30)), ((9, 13), (14, 24))):
+        _, _, rows = rn.fused_reconstruct_rows(10, 4, [i not in lost for i in range(14)])
+        assert stats(run_case(tool, rows, extra=("--share-powers", "--search-basis"))) == want, lost
+    rng = np.random.default_rng(5)
+    for r in (2, 3, 4):
+        run_case(tool, rng.integers(0, 256, (r, 10)), extra=("--share-powers", "--search-basis", "--step-cost", "4"))
