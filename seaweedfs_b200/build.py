@@ -51,6 +51,7 @@ def _stamp() -> str:
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(os.environ.get("SWEC_EXTRA_NVCC_FLAGS", "").encode())
+    h.update(os.environ.get("SWEC_CODEGEN_FLAGS", "").encode())
     return h.hexdigest()
 
 
@@ -59,8 +60,11 @@ def generate() -> None:
     tool = os.path.join(GEN, "swec_codegen")
     _run(["g++", "-O2", "-std=c++17", "-o", tool] +
          [os.path.join(CSRC, s) for s in ("codegen_main.cc", "codegen.cc", "gf256.cc")])
-    out = subprocess.run([tool, "--rs", "10", "4", "--name", "Rs10x4Encode"], check=True,
-                         stdout=subprocess.PIPE, text=True).stdout
+    # SWEC_CODEGEN_FLAGS="--share-powers --search-basis" builds the kernels with the CPU-verified but not yet measured
+    # formulation of DESIGN.md §9.4 (default: none — the shipped kernels are the ones measured on the B200)
+    gen_flags = os.environ.get("SWEC_CODEGEN_FLAGS", "").split()
+    out = subprocess.run([tool, "--rs", "10", "4", "--name", "Rs10x4Encode"] + gen_flags, check=True,
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     with open(os.path.join(GEN, "gen_rs10x4_encode.inc"), "w") as f:
         f.write(out)
     # the same combiner under a second name: kernels.cu binds it to the low-power multiply-by-2 step
@@ -68,7 +72,8 @@ def generate() -> None:
         f.write(out.replace("struct Rs10x4Encode ", "struct Rs10x4EncodeLP "))
     # reconstruct matrices compiled ahead of time (aot_recon.cu): combiners + the matrix table they are found by
     for emit, name in (("structs", "gen_aot_recon.inc"), ("keys", "gen_aot_recon_keys.inc")):
-        text = subprocess.run([tool, "--aot-recon", "10", "4", "--emit", emit], check=True,
+        text = subprocess.run([tool, "--aot-recon", "10", "4", "--emit", emit] +
+                              [f for f in gen_flags if f == "--share-powers"], check=True,
                               stdout=subprocess.PIPE, text=True).stdout
         with open(os.path.join(GEN, name), "w") as f:
             f.write(text)
