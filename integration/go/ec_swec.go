@@ -397,7 +397,7 @@ func (v *swecEcVolume) DeleteNeedleFromEcx(id uint64) error {
 //
 // The n slices are cut from ONE pinned, GPU-mapped allocation on the GPU's NUMA node at a constant pitch: the library
 // recognises that shape and moves all k inputs (and all m outputs) with one strided DMA each way, or — for calls up to
-// 4 MiB per shard — runs the kernel directly on the host memory over PCIe (include/swec.h "host_zero_copy").
+// 2 MiB per shard — runs the kernel directly on the host memory over PCIe (include/swec.h "host_zero_copy").
 // The memory is C memory: no Pinner, no cgo pointer-passing rules, and the slices must not outlive release().
 func swecAllocShardBuffers(n int, shardLen int) (bufs [][]byte, release func()) {
 	pitch := (shardLen + 4095) &^ 4095
